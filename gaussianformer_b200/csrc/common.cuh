@@ -1,0 +1,194 @@
+// Shared device/host helpers for the sm_100a kernels (splat + deformable aggregation).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gf_b200.h"
+
+namespace gf {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (host)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define GF_CUDA_TRY(expr)                                         \
+    do {                                                          \
+        cudaError_t _e = (expr);                                  \
+        if (_e != cudaSuccess) return ::gf::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define GF_REQUIRE(cond, code, ...)      \
+    do {                                 \
+        if (!(cond)) {                   \
+            ::gf::set_error(__VA_ARGS__); \
+            return (code);               \
+        }                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// geometry of the splat pipeline
+// ---------------------------------------------------------------------------------------------
+constexpr int kBinX = 8;        // render CTA footprint in columns: 8 (x) by 4 (y) ...
+constexpr int kBinY = 4;
+constexpr int kBinZ = 16;       // ... by 16 voxels in z (one z-chunk)
+constexpr int kRenderThreads = 128;
+constexpr int kVox = 4;         // voxels per thread (a z-quad)
+constexpr int kChunk = 32;      // Gaussian records staged per TMA batch
+constexpr int kSeg = 512;       // bin-list entries resolved per segment
+constexpr int kGeomFloats = 12; // mu(3) k(1) c6(6) pad(2)
+
+__host__ __device__ constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
+__host__ __device__ constexpr int rec_floats(int C) { return kGeomFloats + round_up(C, 4); }
+
+// Integer box of one Gaussian, inclusive bounds packed lo | hi << 16 per axis; w = 1 when the
+// clipped box is empty.  (reference: getRect, model/head/localagg/src/auxiliary.h:8-20)
+struct __align__(16) PackedBox {
+    uint32_t x, y, z, empty;
+};
+
+struct SplatWorkspace {
+    // all pointers carved out of the caller's workspace by carve_forward_workspace()
+    uint32_t *flags;       // [16]  status word(s)
+    uint32_t *pack_flags;  // [pack_ctas] per-CTA error bits of the pack kernel
+    float *records;        // [G, rec_floats(C)]
+    PackedBox *boxes;      // [G]
+    uint32_t *masks;       // [nsuper, nwords] bit g of supertile s: box(g) overlaps s
+    int32_t *lists;        // [nsuper, G] ascending Gaussian indices per supertile
+    int32_t *counts;       // [nsuper]
+    int st;                // supertile edge (columns)
+    int nsx, nsy, nsuper;  // supertile grid
+    int nwords;            // ceil(G/32)
+    int pack_ctas;
+    size_t bytes;
+};
+
+constexpr int kPackThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk async copy global -> shared through the TMA unit, completion counted on an mbarrier.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// ((v - origin) / cell) truncated toward zero, with the exact fp32 operation order of
+// `((x - pc_min) / grid_size).to(torch.int)` (local_aggregate/__init__.py:137,139).
+__device__ __forceinline__ int voxel_coord(float v, float origin, float cell) {
+    return static_cast<int>(__fdiv_rn(__fsub_rn(v, origin), cell));
+}
+
+// Integer box of Gaussian g (inclusive bounds, clipped to the grid) and the error bits the
+// reference asserts on.  Fuses the Python host preparation (trunc voxel index of the mean, ceil
+// radius; local_aggregate/__init__.py:139-142, prob: :151-153, prob_fast: :151) with getRect
+// (src/auxiliary.h:8-20).  Returns true when the clipped box is empty.
+__device__ __forceinline__ bool gaussian_box(const gf_splat_desc &d, const gf_splat_inputs &in, int g,
+                                             const float mu[3], int lo[3], int hi[3], uint32_t &err) {
+    const int dims[3] = {d.H, d.W, d.D};
+    int m[3], r[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        m[a] = in.means_int ? in.means_int[3 * g + a] : voxel_coord(mu[a], d.pc_min[a], d.grid_size);
+    if (in.radii) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) r[a] = (d.radii_axes == 3) ? in.radii[3 * g + a] : in.radii[g];
+    } else {
+        const float s[3] = {in.scales[3 * g], in.scales[3 * g + 1], in.scales[3 * g + 2]};
+        if (d.radii_axes == 3) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                r[a] = static_cast<int>(ceilf(__fdiv_rn(__fmul_rn(s[a], d.scale_multiplier), d.grid_size)));
+        } else {
+            const float smax = fmaxf(s[0], fmaxf(s[1], s[2]));
+            r[0] = r[1] = r[2] = static_cast<int>(ceilf(__fdiv_rn(__fmul_rn(smax, d.scale_multiplier), d.grid_size)));
+        }
+        if (d.radii_min > 0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) r[a] = max(r[a], d.radii_min);
+        }
+    }
+    bool empty = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (m[a] < 0 || m[a] >= dims[a]) err |= GF_FLAG_MEAN_OUT_OF_GRID;
+        if (r[a] < 1) err |= GF_FLAG_RADIUS_LT_1;
+        // inclusive form of [min(dim,max(0,m-r)), min(dim,max(0,m+r+1)))
+        const long long l = static_cast<long long>(m[a]) - r[a];
+        const long long h = static_cast<long long>(m[a]) + r[a];
+        lo[a] = static_cast<int>(l < 0 ? 0 : l);
+        hi[a] = static_cast<int>(h > dims[a] - 1 ? dims[a] - 1 : h);
+        if (l > dims[a] - 1 || h < 0 || lo[a] > hi[a]) empty = true;
+    }
+    return empty;
+}
+
+// the six inverse-covariance entries (xx,yy,zz,xy,yz,xz) of Gaussian g
+__device__ __forceinline__ void load_cov6(const gf_splat_desc &d, const float *cov, int g, float c6[6]) {
+    const float *cv = cov + static_cast<size_t>(g) * d.cov_stride;
+    if (d.cov_stride == 9) {  // flat entries [0,4,8,1,5,2] of the row-major 3x3 (__init__.py:143)
+        c6[0] = cv[0]; c6[1] = cv[4]; c6[2] = cv[8]; c6[3] = cv[1]; c6[4] = cv[5]; c6[5] = cv[2];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) c6[i] = cv[i];
+    }
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kKappa = 0.06349363593424097f;  // powf(2 * 3.1415926535f, -1.5f), localagg_prob/src/forward.cu:78
+
+#endif  // __CUDACC__
+
+}  // namespace gf

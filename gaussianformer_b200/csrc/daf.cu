@@ -1,0 +1,221 @@
+// Deformable multi-camera / multi-scale aggregation (replaces deformable_aggregation_kernel and
+// deformable_aggregation_grad_kernel, model/encoder/gaussian_encoder/ops/src/deformable_aggregation_cuda.cu:125-259).
+//
+// The reference runs one thread per output scalar: every thread re-reads the sampling location, the
+// level table and its weight, and the backward issues one scalar atomic per corner, per weight and
+// per location from every channel thread.  Here one WARP owns one sampling point:
+//   * lanes span the channel vector in float4 slices, so each of the 4 bilinear corners is one
+//     coalesced 16-byte-per-lane read of a 512-byte feature row (channels-last layout);
+//   * the camera gate and all bilinear coefficients are warp-uniform;
+//   * backward: feature gradients go out as 16-byte vector atomics (one per lane per corner),
+//     weight gradients are reduced over the lanes of a group with shuffles and written by one
+//     lane, location gradients are reduced over the warp — no scalar atomic storms.
+#include "common.cuh"
+
+namespace gf {
+
+constexpr int kDafThreads = 256;
+constexpr int kMaxLevels = 8;
+
+struct DafParams {
+    gf_daf_desc d;
+    const float *feat;
+    const int32_t *shape;
+    const int32_t *start;
+    const float *loc;
+    const float *weights;
+    float *out;               // forward
+    const float *grad_out;    // backward
+    float *grad_feat, *grad_loc, *grad_weights;
+};
+
+struct Bilinear {
+    float w[4];          // corner weights (tl, tr, bl, br)
+    long long row[4];    // feature row of each corner inside the level
+    bool ok[4];
+    float lh, lw, hh, hw;
+};
+
+__device__ __forceinline__ Bilinear bilinear_setup(float lx, float ly, int h, int w) {
+    Bilinear b;
+    const float y_im = ly * static_cast<float>(h) - 0.5f;
+    const float x_im = lx * static_cast<float>(w) - 0.5f;
+    const float yf = floorf(y_im), xf = floorf(x_im);
+    const int y0 = static_cast<int>(yf), x0 = static_cast<int>(xf);
+    b.lh = y_im - yf; b.lw = x_im - xf;
+    b.hh = 1.f - b.lh; b.hw = 1.f - b.lw;
+    b.ok[0] = y0 >= 0 && x0 >= 0;
+    b.ok[1] = y0 >= 0 && x0 + 1 <= w - 1;
+    b.ok[2] = y0 + 1 <= h - 1 && x0 >= 0;
+    b.ok[3] = y0 + 1 <= h - 1 && x0 + 1 <= w - 1;
+    b.row[0] = static_cast<long long>(y0) * w + x0;
+    b.row[1] = b.row[0] + 1;
+    b.row[2] = b.row[0] + w;
+    b.row[3] = b.row[2] + 1;
+    b.w[0] = b.hh * b.hw; b.w[1] = b.hh * b.lw; b.w[2] = b.lh * b.hw; b.w[3] = b.lh * b.lw;
+    return b;
+}
+
+template <int VEC> struct Vec;
+template <> struct Vec<4> {
+    using T = float4;
+    static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ T load(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+    static __device__ __forceinline__ void fma(T &a, float s, const T &v) {
+        a.x = fmaf(s, v.x, a.x); a.y = fmaf(s, v.y, a.y); a.z = fmaf(s, v.z, a.z); a.w = fmaf(s, v.w, a.w);
+    }
+    static __device__ __forceinline__ float dot(const T &a, const T &b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+    static __device__ __forceinline__ void store(float *p, const T &v) { *reinterpret_cast<float4 *>(p) = v; }
+    static __device__ __forceinline__ void atomic_add_scaled(float *p, float s, const T &v) {
+        atomicAdd(reinterpret_cast<float4 *>(p), make_float4(s * v.x, s * v.y, s * v.z, s * v.w));
+    }
+};
+template <> struct Vec<1> {
+    using T = float;
+    static __device__ __forceinline__ T zero() { return 0.f; }
+    static __device__ __forceinline__ T load(const float *p) { return __ldg(p); }
+    static __device__ __forceinline__ void fma(T &a, float s, const T &v) { a = fmaf(s, v, a); }
+    static __device__ __forceinline__ float dot(const T &a, const T &b) { return a * b; }
+    static __device__ __forceinline__ void store(float *p, const T &v) { *p = v; }
+    static __device__ __forceinline__ void atomic_add_scaled(float *p, float s, const T &v) { atomicAdd(p, s * v); }
+};
+
+// VEC = 4: C % 128 == 0 and (C/Gr)/4 a power of two <= 32 (a group is a run of whole lanes).
+// VEC = 1: any C, Gr.
+template <int VEC, bool BACKWARD>
+__global__ void __launch_bounds__(kDafThreads) daf_kernel(const DafParams p) {
+    using V = Vec<VEC>;
+    using T = typename V::T;
+    const int lane = threadIdx.x & 31;
+    const int C = p.d.num_embeds, M = p.d.num_cams, L = p.d.num_scale, Gr = p.d.num_groups, F = p.d.num_feat;
+    const int gdim = C / Gr;
+    const long long npts = static_cast<long long>(p.d.batch) * p.d.num_pts;
+    const long long warps = static_cast<long long>(gridDim.x) * (kDafThreads / 32);
+    int lh[kMaxLevels], lw[kMaxLevels], ls[kMaxLevels];
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l)
+        if (l < L) { lh[l] = p.shape[2 * l]; lw[l] = p.shape[2 * l + 1]; ls[l] = p.start[l]; }
+
+    for (long long bp = static_cast<long long>(blockIdx.x) * (kDafThreads / 32) + (threadIdx.x >> 5); bp < npts; bp += warps) {
+        const int b = static_cast<int>(bp / p.d.num_pts);
+        const float *locp = p.loc + bp * M * 2;  // (x,y) per camera; broadcast loads
+        for (int c0 = lane * VEC; c0 < C; c0 += 32 * VEC) {
+            const int grp = c0 / gdim;
+            T acc = V::zero();
+            T gout = V::zero();
+            if (BACKWARD) gout = V::load(p.grad_out + bp * C + c0);
+            for (int m = 0; m < M; ++m) {
+                const float lx = __ldg(locp + 2 * m), ly = __ldg(locp + 2 * m + 1);
+                if (!(lx > 0.f && lx < 1.f && ly > 0.f && ly < 1.f)) continue;  // warp-uniform
+                const float *fcam = p.feat + (static_cast<long long>(b) * M + m) * F * C + c0;
+                const long long wbase = (bp * M + m) * static_cast<long long>(L) * Gr + grp;
+                float gx = 0.f, gy = 0.f;
+#pragma unroll 4
+                for (int l = 0; l < L; ++l) {
+                    const Bilinear bl = bilinear_setup(lx, ly, lh[l], lw[l]);
+                    const float *flev = fcam + static_cast<long long>(ls[l]) * C;
+                    T v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = bl.ok[k] ? V::load(flev + bl.row[k] * C) : V::zero();
+                    const float wt = __ldg(p.weights + wbase + static_cast<long long>(l) * Gr);
+                    if (!BACKWARD) {
+                        T val = V::zero();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) V::fma(val, bl.w[k], v[k]);
+                        V::fma(acc, wt, val);
+                    } else {
+                        // d(out)/d(feat corner) = bilinear weight * aggregation weight
+                        float *gf = p.grad_feat + (fcam - p.feat) + static_cast<long long>(ls[l]) * C;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (bl.ok[k]) V::atomic_add_scaled(gf + bl.row[k] * C, bl.w[k] * wt, gout);
+                        // d(out)/d(weight) = sampled value
+                        T val = V::zero();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) V::fma(val, bl.w[k], v[k]);
+                        float gw = V::dot(gout, val);
+                        // d(out)/d(x_im), d(out)/d(y_im)   (cuda.cu:85-121)
+                        T dvx = V::zero(), dvy = V::zero();
+                        V::fma(dvx, -bl.hh, v[0]); V::fma(dvx, bl.hh, v[1]); V::fma(dvx, -bl.lh, v[2]); V::fma(dvx, bl.lh, v[3]);
+                        V::fma(dvy, -bl.hw, v[0]); V::fma(dvy, -bl.lw, v[1]); V::fma(dvy, bl.hw, v[2]); V::fma(dvy, bl.lw, v[3]);
+                        gx = fmaf(static_cast<float>(lw[l]) * wt, V::dot(gout, dvx), gx);
+                        gy = fmaf(static_cast<float>(lh[l]) * wt, V::dot(gout, dvy), gy);
+                        if (VEC == 4) {
+                            const int lanes_per_group = gdim / 4;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1)
+                                if (o < lanes_per_group) gw += __shfl_xor_sync(0xffffffffu, gw, o);
+                            if ((lane & (lanes_per_group - 1)) == 0) p.grad_weights[wbase + static_cast<long long>(l) * Gr] += gw;
+                        } else {
+                            atomicAdd(p.grad_weights + wbase + static_cast<long long>(l) * Gr, gw);
+                        }
+                    }
+                }
+                if (BACKWARD) {
+                    float *gl = p.grad_loc + (bp * M + m) * 2;
+                    if (VEC == 4) {  // all 32 lanes are here (C % 128 == 0)
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            gx += __shfl_xor_sync(0xffffffffu, gx, o);
+                            gy += __shfl_xor_sync(0xffffffffu, gy, o);
+                        }
+                        if (lane == 0) {
+                            // with several channel slices (C > 128) each slice adds its share in turn
+                            gl[0] += gx;
+                            gl[1] += gy;
+                        }
+                    } else {
+                        atomicAdd(gl, gx);
+                        atomicAdd(gl + 1, gy);
+                    }
+                }
+            }
+            if (!BACKWARD) V::store(p.out + bp * C + c0, acc);
+        }
+    }
+}
+
+static bool vec4_ok(const gf_daf_desc &d) {
+    if (d.num_embeds % 128 != 0) return false;
+    const int gdim = d.num_embeds / d.num_groups;
+    if (gdim % 4 != 0) return false;
+    const int lpg = gdim / 4;
+    return lpg <= 32 && (lpg & (lpg - 1)) == 0;
+}
+
+int launch_daf(const gf_daf_desc &d, const DafParams &dp, bool backward, int num_sms, cudaStream_t stream) {
+    const long long npts = static_cast<long long>(d.batch) * d.num_pts;
+    if (npts == 0) return GF_OK;
+    const int per_cta = kDafThreads / 32;
+    long long want = (npts + per_cta - 1) / per_cta;
+    const long long cap = static_cast<long long>(num_sms) * 64;
+    const int grid = static_cast<int>(want < cap ? want : cap);
+    const bool v4 = vec4_ok(d);
+    if (backward) {
+        if (v4) daf_kernel<4, true><<<grid, kDafThreads, 0, stream>>>(dp);
+        else daf_kernel<1, true><<<grid, kDafThreads, 0, stream>>>(dp);
+    } else {
+        if (v4) daf_kernel<4, false><<<grid, kDafThreads, 0, stream>>>(dp);
+        else daf_kernel<1, false><<<grid, kDafThreads, 0, stream>>>(dp);
+    }
+    GF_CUDA_TRY(cudaGetLastError());
+    return GF_OK;
+}
+
+int launch_daf_forward(const gf_daf_desc &d, const float *feat, const int32_t *shape, const int32_t *start,
+                       const float *loc, const float *weights, float *out, int num_sms, cudaStream_t stream) {
+    DafParams dp{};
+    dp.d = d; dp.feat = feat; dp.shape = shape; dp.start = start; dp.loc = loc; dp.weights = weights; dp.out = out;
+    return launch_daf(d, dp, false, num_sms, stream);
+}
+
+int launch_daf_backward(const gf_daf_desc &d, const float *feat, const int32_t *shape, const int32_t *start,
+                        const float *loc, const float *weights, const float *grad_out, float *grad_feat,
+                        float *grad_loc, float *grad_weights, int num_sms, cudaStream_t stream) {
+    DafParams dp{};
+    dp.d = d; dp.feat = feat; dp.shape = shape; dp.start = start; dp.loc = loc; dp.weights = weights;
+    dp.grad_out = grad_out; dp.grad_feat = grad_feat; dp.grad_loc = grad_loc; dp.grad_weights = grad_weights;
+    return launch_daf(d, dp, true, num_sms, stream);
+}
+
+}  // namespace gf

@@ -1,0 +1,235 @@
+// Splat stage 1 — per-Gaussian packing and supertile binning (no host synchronisation, no sort).
+//
+// The reference builds a (voxel, Gaussian) pair list, radix-sorts it and needs a blocking D2H copy
+// of the pair count in the middle (model/head/localagg/src/aggregator_impl.cu:193-230).  Here:
+//
+//   pack_mask_kernel   one thread per Gaussian: fuses the reference's Python host preparation
+//                      (trunc voxel index of the mean, ceil radius, 3x3 -> 6 gather;
+//                      local_aggregate/__init__.py:137-143) with FORWARD::preprocess
+//                      (src/forward.cu:9-28): writes a 128-byte record (mean, exponent
+//                      coefficients pre-scaled by log2(e), amplitude, class vector), the clipped
+//                      integer box, and one ballot bit per supertile (16x16 columns) it overlaps.
+//   list_kernel        one CTA per supertile: popcount-scan of the mask words -> ascending
+//                      Gaussian index list (ascending order == the reference's stable sort order).
+#include "common.cuh"
+
+namespace gf {
+
+struct PackParams {
+    gf_splat_desc d;
+    gf_splat_inputs in;
+    float *records;
+    PackedBox *boxes;
+    uint32_t *masks;
+    uint32_t *pack_flags;
+    int rec;     // floats per record
+    int st;      // supertile edge
+    int nsx, nsy;
+    int nwords;
+};
+
+__global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParams p) {
+    const int g = blockIdx.x * kPackThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool live = g < p.d.G;
+
+    uint32_t err = 0;
+    int lo[3] = {1, 1, 1}, hi[3] = {0, 0, 0};
+    bool empty = true;
+    if (live) {
+        const float mu[3] = {p.in.means[3 * g], p.in.means[3 * g + 1], p.in.means[3 * g + 2]};
+        empty = gaussian_box(p.d, p.in, g, mu, lo, hi, err);
+        PackedBox b;
+        b.x = empty ? 1u : (static_cast<uint32_t>(lo[0]) | static_cast<uint32_t>(hi[0]) << 16);
+        b.y = empty ? 1u : (static_cast<uint32_t>(lo[1]) | static_cast<uint32_t>(hi[1]) << 16);
+        b.z = empty ? 1u : (static_cast<uint32_t>(lo[2]) | static_cast<uint32_t>(hi[2]) << 16);
+        b.empty = empty ? 1u : 0u;
+        p.boxes[g] = b;
+
+        // ---- record -------------------------------------------------------------------------
+        float c6[6];
+        load_cov6(p.d, p.in.cov, g, c6);
+        const float a_ = c6[0], b_ = c6[1], c_ = c6[2], d_ = c6[3], e_ = c6[4], f_ = c6[5];
+        float amp = p.in.opacities[g];
+        if (p.d.variant == GF_SPLAT_PROB) {
+            // (2*pi)^-1.5 * sqrt(det) * opacity   (localagg_prob/src/forward.cu:77-78)
+            const float det = a_ * b_ * c_ + 2.f * d_ * e_ * f_ - a_ * e_ * e_ - b_ * f_ * f_ - c_ * d_ * d_;
+            amp = kKappa * sqrtf(det) * amp;
+        }
+        float4 *rec = reinterpret_cast<float4 *>(p.records + static_cast<size_t>(g) * p.rec);
+        rec[0] = make_float4(mu[0], mu[1], mu[2], amp);
+        rec[1] = make_float4(-0.5f * kLog2e * a_, -0.5f * kLog2e * b_, -0.5f * kLog2e * c_, -kLog2e * d_);
+        rec[2] = make_float4(-kLog2e * e_, -kLog2e * f_, 0.f, 0.f);
+        const float *sem = p.in.semantics + static_cast<size_t>(g) * p.d.C;
+        const int nq = (p.rec - kGeomFloats) / 4;
+        for (int q = 0; q < nq; ++q) {
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = (4 * q + i < p.d.C) ? sem[4 * q + i] : 0.f;
+            rec[3 + q] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+
+    // ---- supertile masks: one ballot per supertile, every word is written (no memset needed) ----
+    const int sx0 = empty ? 1 : lo[0] / p.st, sx1 = empty ? 0 : hi[0] / p.st;
+    const int sy0 = empty ? 1 : lo[1] / p.st, sy1 = empty ? 0 : hi[1] / p.st;
+    // warp-wide union of touched supertiles (uniform), so untouched ones cost one store
+    int ux0 = empty ? 0x7fffffff : sx0, ux1 = empty ? -1 : sx1, uy0 = empty ? 0x7fffffff : sy0, uy1 = empty ? -1 : sy1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ux0 = min(ux0, __shfl_xor_sync(0xffffffffu, ux0, o));
+        ux1 = max(ux1, __shfl_xor_sync(0xffffffffu, ux1, o));
+        uy0 = min(uy0, __shfl_xor_sync(0xffffffffu, uy0, o));
+        uy1 = max(uy1, __shfl_xor_sync(0xffffffffu, uy1, o));
+    }
+    const int word = g >> 5;
+    if (word < p.nwords) {
+        for (int sx = 0; sx < p.nsx; ++sx)
+            for (int sy = 0; sy < p.nsy; ++sy) {
+                uint32_t bits = 0;
+                if (sx >= ux0 && sx <= ux1 && sy >= uy0 && sy <= uy1)
+                    bits = __ballot_sync(0xffffffffu, !empty && sx >= sx0 && sx <= sx1 && sy >= sy0 && sy <= sy1);
+                if (lane == 0) p.masks[static_cast<size_t>(sx * p.nsy + sy) * p.nwords + word] = bits;
+            }
+    }
+
+    // ---- per-CTA error bits (plain store; list_kernel folds them into the status word) ----------
+    __shared__ uint32_t s_err;
+    if (threadIdx.x == 0) s_err = 0;
+    __syncthreads();
+    if (err) atomicOr(&s_err, err);
+    __syncthreads();
+    if (threadIdx.x == 0) p.pack_flags[blockIdx.x] = s_err;
+}
+
+struct ListParams {
+    const uint32_t *masks;
+    const uint32_t *pack_flags;
+    int32_t *lists;
+    int32_t *counts;
+    uint32_t *flags;
+    int nwords;
+    int G;
+    int pack_ctas;
+    uint32_t initial_flags;
+};
+
+constexpr int kListThreads = 1024;
+
+__global__ void __launch_bounds__(kListThreads) list_kernel(const ListParams p) {
+    const int s = blockIdx.x;
+    const uint32_t *words = p.masks + static_cast<size_t>(s) * p.nwords;
+    int32_t *list = p.lists + static_cast<size_t>(s) * p.G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int s_warp[kListThreads / 32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int w0 = 0; w0 < p.nwords; w0 += kListThreads) {
+        const int wi = w0 + threadIdx.x;
+        uint32_t bits = wi < p.nwords ? words[wi] : 0u;
+        const int cnt = __popc(bits);
+        int incl = cnt;  // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int warp_off = 0;
+        for (int k = 0; k < warp; ++k) warp_off += s_warp[k];
+        int pos = s_base + warp_off + incl - cnt;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            list[pos++] = wi * 32 + b;
+        }
+        __syncthreads();
+        if (threadIdx.x == kListThreads - 1) s_base = pos;  // last thread holds the running total
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) p.counts[s] = s_base;
+
+    if (s == 0) {  // fold the pack kernel's error bits into the status word (also initialises it)
+        uint32_t e = 0;
+        for (int i = threadIdx.x; i < p.pack_ctas; i += kListThreads) e |= p.pack_flags[i];
+        e = __reduce_or_sync(0xffffffffu, e);
+        __shared__ uint32_t s_e;
+        if (threadIdx.x == 0) s_e = p.initial_flags;
+        __syncthreads();
+        if (lane == 0 && e) atomicOr(&s_e, e);
+        __syncthreads();
+        if (threadIdx.x == 0) p.flags[0] = s_e;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int plan_forward_workspace(const gf_splat_desc &d, void *base, SplatWorkspace *ws) {
+    int st = 16;
+    const size_t budget = size_t(512) << 20;
+    while (true) {
+        const size_t ns = size_t((d.H + st - 1) / st) * size_t((d.W + st - 1) / st);
+        if (ns * size_t(d.G) * 4 <= budget || st >= 1024) break;
+        st *= 2;
+    }
+    ws->st = st;
+    ws->nsx = (d.H + st - 1) / st;
+    ws->nsy = (d.W + st - 1) / st;
+    ws->nsuper = ws->nsx * ws->nsy;
+    ws->nwords = (d.G + 31) / 32;
+    ws->pack_ctas = (d.G + kPackThreads - 1) / kPackThreads;
+    size_t off = 0;
+    char *b = static_cast<char *>(base);
+    auto take = [&](size_t bytes) {
+        char *p = b ? b + off : nullptr;
+        off = align_up(off + bytes, 256);
+        return p;
+    };
+    ws->flags = reinterpret_cast<uint32_t *>(take(64));
+    ws->pack_flags = reinterpret_cast<uint32_t *>(take(size_t(ws->pack_ctas) * 4));
+    ws->records = reinterpret_cast<float *>(take(size_t(d.G) * rec_floats(d.C) * 4));
+    ws->boxes = reinterpret_cast<PackedBox *>(take(size_t(d.G) * sizeof(PackedBox)));
+    ws->masks = reinterpret_cast<uint32_t *>(take(size_t(ws->nsuper) * ws->nwords * 4));
+    ws->lists = reinterpret_cast<int32_t *>(take(size_t(ws->nsuper) * d.G * 4));
+    ws->counts = reinterpret_cast<int32_t *>(take(size_t(ws->nsuper) * 4));
+    ws->bytes = off;
+    return GF_OK;
+}
+
+int launch_prep(const gf_splat_desc &d, const gf_splat_inputs &in, const SplatWorkspace &ws,
+                uint32_t initial_flags, cudaStream_t stream) {
+    PackParams pp;
+    pp.d = d;
+    pp.in = in;
+    pp.records = ws.records;
+    pp.boxes = ws.boxes;
+    pp.masks = ws.masks;
+    pp.pack_flags = ws.pack_flags;
+    pp.rec = rec_floats(d.C);
+    pp.st = ws.st;
+    pp.nsx = ws.nsx;
+    pp.nsy = ws.nsy;
+    pp.nwords = ws.nwords;
+    pack_mask_kernel<<<ws.pack_ctas, kPackThreads, 0, stream>>>(pp);
+    GF_CUDA_TRY(cudaGetLastError());
+    ListParams lp;
+    lp.masks = ws.masks;
+    lp.pack_flags = ws.pack_flags;
+    lp.lists = ws.lists;
+    lp.counts = ws.counts;
+    lp.flags = ws.flags;
+    lp.nwords = ws.nwords;
+    lp.G = d.G;
+    lp.pack_ctas = ws.pack_ctas;
+    lp.initial_flags = initial_flags;
+    list_kernel<<<ws.nsuper, kListThreads, 0, stream>>>(lp);
+    GF_CUDA_TRY(cudaGetLastError());
+    return GF_OK;
+}
+
+}  // namespace gf

@@ -1,0 +1,239 @@
+"""Host-side mirror of the reference's three splat packages.
+
+``LocalAggregator`` keeps the reference's constructor kwargs, buffer name (``pc_min``) and call
+signature (``model/head/localagg/local_aggregate/__init__.py:108-161``,
+``model/head/localagg_prob/local_aggregate_prob/__init__.py:118-169``,
+``model/head/localagg_prob_fast/local_aggregate_prob_fast/__init__.py:151``) so that
+``GaussianHead`` (``model/head/gaussian_head.py:30-39,157-163``) can construct and call it
+unchanged.  The arithmetic — including the reference's Python-side preparation (voxel indices,
+radii, 3x3 -> 6 gather) — runs in the sm_100a kernels behind the C ABI (``include/gf_b200.h``).
+
+Differences from the reference, all supersets:
+
+* batch sizes > 1 are accepted (the reference asserts ``B == 1``); ``B == 1`` returns the same
+  squeezed shapes as the reference;
+* no host synchronisation inside the op except one status-word read when ``validate=True``
+  (the reference performs >= 7 ``.min()/.max()`` syncs plus a blocking memcpy);
+* inputs in any float dtype are computed in fp32 (the reference would throw on half tensors).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import SplatDesc, SplatGrads, SplatInputs, SplatOutputs
+
+_COV_IDX = (0, 4, 8, 1, 5, 2)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _f32c(t):
+    return t.detach().contiguous().float()
+
+
+def _make_desc(G, N, C, H, W, D, variant, radii_axes, cov_stride, pc_min, grid_size, scale_multiplier, radii_min):
+    d = SplatDesc()
+    d.G, d.N, d.C, d.H, d.W, d.D = G, N, C, H, W, D
+    d.variant, d.radii_axes, d.cov_stride = variant, radii_axes, cov_stride
+    d.pc_min[0], d.pc_min[1], d.pc_min[2] = pc_min
+    d.grid_size, d.scale_multiplier, d.radii_min = grid_size, scale_multiplier, radii_min
+    return d
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "gaussianformer_b200 ops are CUDA-only (sm_100a); got a CPU tensor. There is no CPU fallback.")
+
+
+def splat_forward_raw(desc, pts, means, opa, sem, cov, *, points_int=None, means_int=None, radii=None, scales=None):
+    """One sample through ``gf_splat_forward``.  Returns (outputs tuple, workspace tensor)."""
+    L = _lib.lib()
+    dev = pts.device
+    with torch.cuda.device(dev):
+        N, C = desc.N, desc.C
+        logits = torch.empty((N, C), dtype=torch.float32, device=dev)
+        prob = desc.variant == _lib.GF_SPLAT_PROB
+        if prob:
+            aux = torch.empty((3, N), dtype=torch.float32, device=dev)
+            binl, dens, probability = aux[0], aux[1], aux[2]
+        else:
+            binl = dens = probability = None
+        ws_bytes = L.gf_splat_forward_workspace_bytes(ctypes.byref(desc))
+        if ws_bytes == 0:
+            raise _lib.GfError(L.gf_last_error().decode())
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ins = SplatInputs(_ptr(pts), _ptr(points_int), _ptr(means), _ptr(means_int), _ptr(opa), _ptr(sem), _ptr(cov),
+                          _ptr(radii), _ptr(scales))
+        outs = SplatOutputs(_ptr(logits), _ptr(binl), _ptr(dens), _ptr(probability))
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.gf_splat_forward(ctypes.byref(desc), ctypes.byref(ins), ctypes.byref(outs), _ptr(ws), ws_bytes,
+                                      stream))
+    return (logits, binl, dens, probability), ws
+
+
+def splat_backward_raw(desc, pts, means, opa, sem, cov, grads_in, saved, *, points_int=None, means_int=None,
+                       radii=None, scales=None):
+    """One sample through ``gf_splat_backward``.  Returns (g_means[G,3], g_opa[G], g_sem[G,C], g_cov6[G,6])."""
+    L = _lib.lib()
+    dev = pts.device
+    with torch.cuda.device(dev):
+        G, C = desc.G, desc.C
+        gm = torch.empty((G, 3), dtype=torch.float32, device=dev)
+        go = torch.empty((G,), dtype=torch.float32, device=dev)
+        gs = torch.empty((G, C), dtype=torch.float32, device=dev)
+        gc = torch.empty((G, 6), dtype=torch.float32, device=dev)
+        ws_bytes = L.gf_splat_backward_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        ins = SplatInputs(_ptr(pts), _ptr(points_int), _ptr(means), _ptr(means_int), _ptr(opa), _ptr(sem), _ptr(cov),
+                          _ptr(radii), _ptr(scales))
+        g_logits, g_bin, g_dens = grads_in
+        logits, binl, probability = saved
+        gr = SplatGrads(_ptr(g_logits), _ptr(g_bin), _ptr(g_dens), _ptr(logits), _ptr(binl), _ptr(probability),
+                        _ptr(gm), _ptr(go), _ptr(gs), _ptr(gc))
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.gf_splat_backward(ctypes.byref(desc), ctypes.byref(ins), ctypes.byref(gr), _ptr(ws), ws_bytes,
+                                       stream))
+    return gm, go, gs, gc
+
+
+def read_flags(ws, device):
+    flags = ctypes.c_uint32(0)
+    with torch.cuda.device(device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(_lib.lib().gf_splat_read_flags(_ptr(ws), stream, ctypes.byref(flags)))
+    return int(flags.value)
+
+
+def _assert_flags(flags):
+    # same conditions, same exception type as the reference's Python asserts
+    assert not (flags & _lib.GF_FLAG_POINT_OUT_OF_GRID), "points_int outside the voxel grid"
+    assert not (flags & _lib.GF_FLAG_MEAN_OUT_OF_GRID), "means3D_int outside the voxel grid"
+    assert not (flags & _lib.GF_FLAG_RADIUS_LT_1), "radii.min() < 1"
+
+
+class _SplatFunction(torch.autograd.Function):
+    """Per-sample autograd bridge (reference: ``_LocalAggregate``, ``__init__.py:18-106``).
+
+    Saves only the user tensors (+ the prob outputs); the backward kernels need no scratch kept
+    alive from the forward, unlike the reference's three byte buffers (``__init__.py:53-63``).
+    """
+
+    @staticmethod
+    def forward(ctx, pts, means, opa, sem, scales, cov, cfg):
+        desc = _make_desc(means.shape[0], pts.shape[0], sem.shape[1], cfg["H"], cfg["W"], cfg["D"], cfg["variant"],
+                          cfg["radii_axes"], 9, cfg["pc_min"], cfg["grid_size"], cfg["scale_multiplier"],
+                          cfg["radii_min"])
+        pts_c, means_c, opa_c, sem_c, scales_c = map(_f32c, (pts, means, opa, sem, scales))
+        cov_c = _f32c(cov).reshape(-1, 9)
+        (logits, binl, dens, probability), ws = splat_forward_raw(desc, pts_c, means_c, opa_c, sem_c, cov_c,
+                                                                 scales=scales_c)
+        if cfg["validate"]:
+            _assert_flags(read_flags(ws, pts.device))
+        ctx.desc = desc
+        ctx.prob = cfg["variant"] == _lib.GF_SPLAT_PROB
+        if ctx.prob:
+            ctx.save_for_backward(pts_c, means_c, opa_c, sem_c, scales_c, cov_c, logits, binl, probability)
+            ctx.mark_non_differentiable(probability)
+            return logits, binl, dens, probability
+        ctx.save_for_backward(pts_c, means_c, opa_c, sem_c, scales_c, cov_c)
+        return logits
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        if ctx.prob:
+            pts, means, opa, sem, scales, cov, logits, binl, probability = ctx.saved_tensors
+            g_logits, g_bin, g_dens = (None if g is None else _f32c(g) for g in grad_outputs[:3])
+            N, C = logits.shape
+            if g_logits is None:
+                g_logits = torch.zeros((N, C), dtype=torch.float32, device=pts.device)
+            if g_bin is None:
+                g_bin = torch.zeros((N,), dtype=torch.float32, device=pts.device)
+            if g_dens is None:
+                g_dens = torch.zeros((N,), dtype=torch.float32, device=pts.device)
+            grads_in, saved = (g_logits, g_bin, g_dens), (logits, binl, probability)
+        else:
+            pts, means, opa, sem, scales, cov = ctx.saved_tensors
+            grads_in, saved = (_f32c(grad_outputs[0]), None, None), (None, None, None)
+        gm, go, gs, gc6 = splat_backward_raw(ctx.desc, pts, means, opa, sem, cov, grads_in, saved, scales=scales)
+        # the 6 gathered entries receive gradient, the rest of the 3x3 gets zero (indexing autograd
+        # in the reference: cov3D.flatten(1)[:, [0,4,8,1,5,2]])
+        gcov = torch.zeros((gc6.shape[0], 9), dtype=torch.float32, device=gc6.device)
+        gcov[:, list(_COV_IDX)] = gc6
+        return None, gm, go, gs, None, gcov.reshape(-1, 3, 3), None
+
+
+class _LocalAggregatorBase(nn.Module):
+    _variant = _lib.GF_SPLAT_BASE
+    _radii_axes = 1
+
+    def _setup(self, scale_multiplier, H, W, D, pc_min, grid_size, radii_min):
+        self.scale_multiplier = scale_multiplier
+        self.H, self.W, self.D = H, W, D
+        self.register_buffer("pc_min", torch.tensor(pc_min, dtype=torch.float).unsqueeze(0))
+        self._pc_min_host = tuple(float(v) for v in pc_min)
+        self.grid_size = grid_size
+        self.radii_min = radii_min
+        #: read the device status word after each forward and raise AssertionError like the
+        #: reference's asserts (one sync).  Set False for fully asynchronous / graph-captured use.
+        self.validate = os.environ.get("GF_B200_VALIDATE", "1") != "0"
+        _lib.lib()  # fail loudly at construction time if the extension is missing
+
+    def _cfg(self):
+        return dict(H=self.H, W=self.W, D=self.D, variant=self._variant, radii_axes=self._radii_axes,
+                    pc_min=self._pc_min_host, grid_size=float(self.grid_size),
+                    scale_multiplier=float(self.scale_multiplier),
+                    radii_min=int(self.radii_min) if self.radii_min is not None else 0, validate=self.validate)
+
+    def _run(self, pts, means3D, opacities, semantics, scales, cov3D):
+        _require_cuda(pts, means3D, opacities, semantics, scales, cov3D)
+        assert not pts.requires_grad
+        B = pts.shape[0]
+        cfg = self._cfg()
+        outs = []
+        for b in range(B):
+            outs.append(_SplatFunction.apply(pts[b], means3D[b], opacities[b], semantics[b],
+                                             scales[b].detach(), cov3D[b], cfg))
+        return outs
+
+
+class LocalAggregator(_LocalAggregatorBase):
+    """Drop-in for ``local_aggregate.LocalAggregator``: forward(...) -> logits [N, C]."""
+
+    def __init__(self, scale_multiplier, H, W, D, pc_min, grid_size, inv_softmax=False):
+        super().__init__()
+        self._setup(scale_multiplier, H, W, D, pc_min, grid_size, radii_min=None)
+        self.inv_softmax = inv_softmax
+
+    def forward(self, pts, means3D, opacities, semantics, scales, cov3D):
+        outs = self._run(pts, means3D, opacities, semantics, scales, cov3D)
+        assert not self.inv_softmax  # the reference's `assert False` branch
+        return outs[0] if len(outs) == 1 else torch.stack(outs, 0)
+
+
+class LocalAggregatorProb(_LocalAggregatorBase):
+    """Drop-in for ``local_aggregate_prob.LocalAggregator``: -> (logits [N,C], bin_logits [N], density [N])."""
+    _variant = _lib.GF_SPLAT_PROB
+
+    def __init__(self, scale_multiplier, H, W, D, pc_min, grid_size, radii_min=1):
+        super().__init__()
+        self._setup(scale_multiplier, H, W, D, pc_min, grid_size, radii_min=radii_min)
+
+    def forward(self, pts, means3D, opas, semantics, scales, cov3D):
+        outs = self._run(pts, means3D, opas, semantics, scales, cov3D)
+        if len(outs) == 1:
+            return outs[0][0], outs[0][1], outs[0][2]
+        return tuple(torch.stack([o[i] for o in outs], 0) for i in range(3))
+
+
+class LocalAggregatorProbFast(LocalAggregatorProb):
+    """Drop-in for ``local_aggregate_prob_fast.LocalAggregator`` (per-axis integer radii)."""
+    _radii_axes = 3

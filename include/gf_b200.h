@@ -1,0 +1,166 @@
+/*
+ * gf_b200.h — C ABI of the B200-native GaussianFormer hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer is a DEVICE pointer unless it
+ * says "host".  Every entry point is asynchronous on the given stream and returns a GF_* status;
+ * gf_last_error() gives the message for the calling thread.  The library never allocates or
+ * frees device memory: scratch is a caller-provided workspace whose size comes from the matching
+ * *_workspace_bytes() query (the reference instead grows torch byte tensors through
+ * std::function callbacks — model/head/localagg/local_aggregate.cu:27-33,58-63).
+ *
+ * What each entry point replaces in the reference (paths relative to the reference tree):
+ *
+ *   gf_splat_forward   LocalAggregator::Aggregator::forward
+ *                        model/head/localagg/src/aggregator.h:24-41, src/aggregator_impl.cu:152-252
+ *                        model/head/localagg_prob/src/aggregator.h (variant = GF_SPLAT_PROB)
+ *                        model/head/localagg_prob_fast/src/auxiliary.h:8-20 (radii_axes = 3)
+ *                      plus, when the *_int / radii pointers are NULL, the host preparation of
+ *                        model/head/localagg/local_aggregate/__init__.py:137-143
+ *   gf_splat_backward  LocalAggregator::Aggregator::backward
+ *                        model/head/localagg/src/aggregator.h:43-61, src/aggregator_impl.cu:256-307
+ *                        model/head/localagg_prob/src/backward.cu:24-123 (variant = GF_SPLAT_PROB)
+ *   gf_daf_forward     deformable_aggregation()
+ *                        model/encoder/gaussian_encoder/ops/src/deformable_aggregation.cpp:4-18
+ *                        .../ops/src/deformable_aggregation_cuda.cu:262-284
+ *   gf_daf_backward    deformable_aggregation_grad()
+ *                        .../ops/src/deformable_aggregation.cpp:20-38, ..._cuda.cu:287-313
+ *
+ * The ABI is a superset of those boundaries: explicit stream, explicit class count C (the
+ * reference hard-codes NUM_CHANNELS 18, model/head/localagg/src/config.h:15), 64-bit safe sizes,
+ * caller-owned workspace and an int status.
+ */
+#ifndef GF_B200_H_
+#define GF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GF_ABI_VERSION 1
+
+/* status codes */
+#define GF_OK 0
+#define GF_ERR_INVALID_ARG 1   /* bad shape / NULL pointer / unsupported combination */
+#define GF_ERR_WORKSPACE 2     /* workspace NULL, misaligned or smaller than *_workspace_bytes() */
+#define GF_ERR_CUDA 3          /* a CUDA runtime call failed (message has cudaGetErrorString) */
+#define GF_ERR_UNSUPPORTED 4   /* e.g. class count outside the compiled range */
+
+/* splat variants */
+#define GF_SPLAT_BASE 0        /* local_aggregate:            logits                       */
+#define GF_SPLAT_PROB 1        /* local_aggregate_prob(_fast): logits, bin_logits, density  */
+
+/* bits of the device-side status word (gf_splat_read_flags) — the conditions the reference's
+ * Python wrapper asserts on (local_aggregate/__init__.py:138,140,142) */
+#define GF_FLAG_POINT_OUT_OF_GRID 1u
+#define GF_FLAG_MEAN_OUT_OF_GRID 2u
+#define GF_FLAG_RADIUS_LT_1 4u
+#define GF_FLAG_GENERIC_PATH 256u /* informational: points were not in canonical voxel order */
+
+typedef void *gf_stream_t; /* a cudaStream_t (NULL = legacy default stream) */
+
+typedef struct gf_splat_desc {
+    int32_t G;          /* Gaussians (P in the reference) */
+    int32_t N;          /* query points */
+    int32_t C;          /* classes / channels (18 for nuScenes-SurroundOcc) */
+    int32_t H, W, D;    /* voxel grid */
+    int32_t variant;    /* GF_SPLAT_BASE | GF_SPLAT_PROB */
+    int32_t radii_axes; /* 1: one radius per Gaussian, 3: per-axis radii (prob_fast) */
+    int32_t cov_stride; /* floats per Gaussian in `cov`: 6 = (xx,yy,zz,xy,yz,xz); 9 = row-major
+                           3x3 from which entries [0,4,8,1,5,2] are taken (__init__.py:143) */
+    /* host-preparation parameters, used when points_int / means_int / radii are NULL */
+    float pc_min[3];
+    float grid_size;
+    float scale_multiplier;
+    int32_t radii_min;  /* <=0: no clamp (base variant); >=1: radii.clamp(min) (prob variants) */
+} gf_splat_desc;
+
+/* Inputs of both passes.  points_int / means_int / radii mirror the reference's native
+ * boundary; pass NULL to have them derived on the device from pts / means / scales exactly as
+ * the reference's Python wrapper does (fp32 subtract, fp32 divide, truncate; ceil for radii). */
+typedef struct gf_splat_inputs {
+    const float *pts;         /* [N,3] */
+    const int32_t *points_int;/* [N,3] or NULL */
+    const float *means;       /* [G,3] */
+    const int32_t *means_int; /* [G,3] or NULL */
+    const float *opacities;   /* [G] */
+    const float *semantics;   /* [G,C] */
+    const float *cov;         /* [G,cov_stride] inverse covariance */
+    const int32_t *radii;     /* [G] or [G,3], or NULL */
+    const float *scales;      /* [G,3]; only read when radii == NULL */
+} gf_splat_inputs;
+
+typedef struct gf_splat_outputs {
+    float *logits;      /* [N,C] */
+    float *bin_logits;  /* [N]  (prob only) */
+    float *density;     /* [N]  (prob only) */
+    float *probability; /* [N]  (prob only; saved for backward like the reference) */
+} gf_splat_outputs;
+
+typedef struct gf_splat_grads {
+    /* upstream */
+    const float *logits_grad;     /* [N,C] */
+    const float *bin_logits_grad; /* [N] (prob only) */
+    const float *density_grad;    /* [N] (prob only) */
+    /* saved forward outputs (prob only) */
+    const float *logits;          /* [N,C] */
+    const float *bin_logits;      /* [N] */
+    const float *probability;     /* [N] */
+    /* results: fully overwritten */
+    float *means_grad;            /* [G,3] */
+    float *opacity_grad;          /* [G] */
+    float *semantics_grad;        /* [G,C] */
+    float *cov_grad;              /* [G,6] in (xx,yy,zz,xy,yz,xz) order */
+} gf_splat_grads;
+
+typedef struct gf_daf_desc {
+    int32_t batch;      /* B */
+    int32_t num_cams;   /* M */
+    int32_t num_feat;   /* F = sum_l h_l*w_l */
+    int32_t num_embeds; /* C */
+    int32_t num_scale;  /* L */
+    int32_t num_pts;    /* P */
+    int32_t num_groups; /* Gr, divides C */
+} gf_daf_desc;
+
+int gf_abi_version(void);
+const char *gf_last_error(void);
+
+/* number of classes the splat kernels were compiled for: returns how many values were written
+ * to out[] (at most cap). */
+int gf_splat_supported_classes(int32_t *out, int cap);
+
+size_t gf_splat_forward_workspace_bytes(const gf_splat_desc *desc);
+size_t gf_splat_backward_workspace_bytes(const gf_splat_desc *desc);
+
+int gf_splat_forward(const gf_splat_desc *desc, const gf_splat_inputs *in,
+                     const gf_splat_outputs *out, void *workspace, size_t workspace_bytes,
+                     gf_stream_t stream);
+
+int gf_splat_backward(const gf_splat_desc *desc, const gf_splat_inputs *in,
+                      const gf_splat_grads *grads, void *workspace, size_t workspace_bytes,
+                      gf_stream_t stream);
+
+/* Copies the status word of the last gf_splat_forward that used `workspace` to *host_flags
+ * (GF_FLAG_* bits) and synchronises the stream.  The reference raises AssertionError from Python
+ * for the same conditions. */
+int gf_splat_read_flags(const void *workspace, gf_stream_t stream, uint32_t *host_flags);
+
+/* out[B,P,C] is fully overwritten. */
+int gf_daf_forward(const gf_daf_desc *desc, const float *mc_ms_feat, const int32_t *spatial_shape,
+                   const int32_t *scale_start_index, const float *sample_location,
+                   const float *weights, float *output, gf_stream_t stream);
+
+/* Accumulates (+=) into the three gradient buffers like the reference's atomics do; the caller
+ * zero-fills them first (ops/deformable_aggregation.py:55-57). */
+int gf_daf_backward(const gf_daf_desc *desc, const float *mc_ms_feat, const int32_t *spatial_shape,
+                    const int32_t *scale_start_index, const float *sample_location,
+                    const float *weights, const float *grad_output, float *grad_mc_ms_feat,
+                    float *grad_sampling_location, float *grad_weights, gf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GF_B200_H_ */

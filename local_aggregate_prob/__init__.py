@@ -1,0 +1,5 @@
+"""Import-name shim: `import local_aggregate_prob` resolves to the B200-native op, so the reference's
+`GaussianHead` (model/head/gaussian_head.py:30-39) constructs it unchanged."""
+from gaussianformer_b200.splat import LocalAggregatorProb as LocalAggregator  # noqa: F401
+
+__all__ = ["LocalAggregator"]

@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — Gaussians->voxels throughput of the splat hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one forward pass of the splat op (pack + supertile binning + render; 4 kernel launches)
+over one synthetic sample of BASELINE.json configs[1]: `nuscenes_gs25600_solid.py` shape —
+25 600 Gaussians (+ the "empty" Gaussian) into the 200x200x16 grid, 18 classes, batch 1 per GPU.
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md "Measurement".
+
+* value        whole-job Gaussians/s with inputs resident in HBM, CUDA-event timed, max over ranks
+* e2e          the same metric through the public module (`local_aggregate.LocalAggregator`) with
+               HOST (pinned) inputs: H2D of every input + forward + argmax + D2H of the occupancy
+               prediction inside the timed region
+* roofline     the tile render kernel timed alone (events recorded around it inside the C ABI),
+               algorithmic bytes 112*G + 84*N   over the measured HBM copy peak
+* cpu_baseline the oracle's C/OpenMP port of the reference algorithm on the host cores (rank 0)
+
+`--impl reference` times that CPU port as the reference arm (the reference has no CPU
+implementation of the splat; its CUDA op cannot run without a GPU build of torch extensions —
+when oracle/_ref was shipped, its timing on this GPU is reported as `ref_cuda_op` in the main line).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "gs25600_solid"
+METRIC = "gaussians_to_voxels_per_sec"
+UNIT = "Gaussians/s"
+G_COUNTED = 25600                 # learned Gaussians per sample (the empty one is overhead)
+N_SETS = 6                        # rotating input/output sets so the working set exceeds L2
+
+
+def _algorithmic_bytes(G, N, C=18):
+    return (3 + 6 + 1 + C) * 4 * G + 12 * N + 4 * C * N      # 112*G + 84*N for C = 18
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self._stop_evt = index, [], set(), threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=10)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def _measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def _cpu_port_once(kw, inp):
+    """One forward of the CPU port (oracle C code, all OpenMP threads).  Returns seconds."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    a = {k: v[0].numpy() for k, v in inp.items()}
+    dims = (kw["H"], kw["W"], kw["D"])
+    t0 = time.perf_counter()
+    pi, mi, radii = oracle.host_prep(a["pts"], a["means"], a["scales"], kw["pc_min"], kw["grid_size"],
+                                     kw["scale_multiplier"])
+    cov6 = oracle.cov6_from_3x3(a["cov"])
+    oracle.splat_forward(a["pts"], pi, a["means"], mi, a["opa"], a["sem"], cov6, radii, dims, "f32")
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    """Reference arm: the reference algorithm's CPU port on this box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from gaussianformer_b200.synthetic import make_splat_inputs
+    kw, inp, _ = make_splat_inputs(WORKLOAD, seed=0, perturb=True)
+    for _ in range(max(1, min(args.warmup, 2))):
+        _cpu_port_once(kw, inp)
+    steps = max(1, min(args.steps, 10))
+    t = [_cpu_port_once(kw, inp) for _ in range(steps)]
+    sec = sum(t) / len(t)
+    value = G_COUNTED / sec
+    cores = oracle.num_threads()
+    sample = f"{steps} full forward passes of the {WORKLOAD} sample (N=640000 points, G=25601)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD}: 25600 Gaussians (+1 empty) -> 200x200x16x18, batch 1"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (bwd, prob, DAF, ref op)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from gaussianformer_b200 import _lib
+    from gaussianformer_b200.splat import _make_desc, _ptr, LocalAggregator
+    from gaussianformer_b200.synthetic import make_splat_inputs
+    import ctypes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback of the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    # ---- resident inputs: N_SETS different samples (seeded), rotated so no step re-reads L2 -------
+    kw, inp0, _ = make_splat_inputs(WORKLOAD, seed=rank * 100, perturb=True)
+    sets = []
+    for i in range(N_SETS):
+        _, inp, _ = (kw, inp0, None) if i == 0 else make_splat_inputs(WORKLOAD, seed=rank * 100 + i, perturb=True)
+        t = {k: v[0].to(dev).contiguous() for k, v in inp.items()}
+        t["cov"] = t["cov"].reshape(-1, 9).contiguous()
+        sets.append(t)
+    G, N, C = sets[0]["means"].shape[0], sets[0]["pts"].shape[0], 18
+    desc = _make_desc(G, N, C, kw["H"], kw["W"], kw["D"], _lib.GF_SPLAT_BASE, 1, 9, kw["pc_min"], kw["grid_size"],
+                      float(kw["scale_multiplier"]), 0)
+    ws_bytes = L.gf_splat_forward_workspace_bytes(ctypes.byref(desc))
+    outs = [torch.empty((N, C), device=dev) for _ in range(N_SETS)]
+    wss = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in range(N_SETS)]
+    stream = torch.cuda.current_stream(dev)
+    sptr = ctypes.c_void_p(stream.cuda_stream)
+    calls = []
+    for t, o, w in zip(sets, outs, wss):
+        ins = _lib.SplatInputs(_ptr(t["pts"]), None, _ptr(t["means"]), None, _ptr(t["opa"]), _ptr(t["sem"]),
+                               _ptr(t["cov"]), None, _ptr(t["scales"]))
+        ou = _lib.SplatOutputs(_ptr(o), None, None, None)
+        calls.append((ins, ou, w))
+    loss_buf = torch.zeros(1, device=dev)
+
+    def step(i):
+        ins, ou, w = calls[i % N_SETS]
+        _lib.check(L.gf_splat_forward(ctypes.byref(desc), ctypes.byref(ins), ctypes.byref(ou), _ptr(w), ws_bytes, sptr))
+        if world > 1:   # north star: NCCL only for the (scalar) loss all-reduce
+            dist.all_reduce(loss_buf)
+
+    def timed_region(nsteps, fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(nsteps):
+            fn(i)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    for i in range(W):
+        step(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms = timed_region(K, step)
+    clocks = sampler.stop()
+    ms_per_step = total_ms / K
+    value = world * G_COUNTED / (ms_per_step * 1e-3)
+
+    # ---- roofline: the render kernel alone, events recorded around it inside the C ABI -----------
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 50))]
+    for i, (a, b) in enumerate(evs):
+        a.record(stream); b.record(stream)          # materialise the underlying cudaEvent_t
+        L.gf_splat_set_render_events(ctypes.c_void_p(a.cuda_event), ctypes.c_void_p(b.cuda_event))
+        step(i)
+    L.gf_splat_set_render_events(None, None)
+    torch.cuda.synchronize(dev)
+    render_ms = sorted(a.elapsed_time(b) for a, b in evs)
+    render_ms = sum(render_ms) / len(render_ms)
+    peak, peak_kind = _measured_peak()
+    alg = _algorithmic_bytes(G, N, C)
+    achieved = alg / (render_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "render_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "render_tile_kernel<18,false>", "kernel_ms": render_ms,
+                "algorithmic_bytes": alg, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)"}
+
+    # ---- e2e: public module, host (pinned) inputs, H2D + forward + argmax + D2H -------------------
+    module = LocalAggregator(**kw).to(dev)
+    module.validate = False     # the D2H read of the prediction below is the step's sync point
+    host = [{k: v.pin_memory() for k, v in (inp0 if i == 0 else make_splat_inputs(WORKLOAD, seed=rank * 100 + i, perturb=True)[1]).items()}
+            for i in range(2)]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    pred_host = torch.empty(N, dtype=torch.uint8).pin_memory()
+    d2h = pred_host.numel()
+
+    def e2e_step(i):
+        hin = host[i % 2]
+        d = {k: v.to(dev, non_blocking=True) for k, v in hin.items()}
+        logits = module(d["pts"], d["means"], d["opa"], d["sem"], d["scales"], d["cov"])
+        pred_host.copy_(logits.argmax(dim=1).to(torch.uint8), non_blocking=True)
+        if world > 1:
+            dist.all_reduce(loss_buf)
+        stream.synchronize()        # the caller consumes the prediction on the host every step
+
+    for i in range(3):
+        e2e_step(i)
+    e2e_steps = max(5, min(K, 50))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    e2e_ms_dev = timed_region(e2e_steps, e2e_step)
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = max(e2e_ms_dev, 0.0) / e2e_steps
+    e2e = {"value": world * G_COUNTED / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall * 1e3 / e2e_steps,
+           "api": "local_aggregate.LocalAggregator.forward (validate=False) + argmax"}
+
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        extras = side_measurements(dev, kw, inp0, sets[0], desc)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        import oracle
+        _cpu_port_once(kw, inp0)
+        reps = [_cpu_port_once(kw, inp0) for _ in range(3)]
+        sec = sum(reps) / len(reps)
+        cpu_baseline = {"value": G_COUNTED / sec, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+                        "sample": f"3 full forward passes of the {WORKLOAD} sample, {sec:.3f} s each (C/OpenMP oracle)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{WORKLOAD}: 25600 Gaussians (+1 empty) -> 200x200x16x18 voxels, "
+                                       f"batch 1 per GPU, perturbed voxel-centre points",
+                           "l2": f"{N_SETS} rotating input/output/workspace sets "
+                                 f"({N_SETS * (alg + ws_bytes) / 1e6:.0f} MB) > 126 MB L2",
+                           "parallelism": f"dp{world} (one sample per GPU, scalar loss all-reduce)"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * K, "roofline": roofline,
+                "cpu_baseline": cpu_baseline}
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def side_measurements(dev, kw, inp0, resident, desc):
+    """Reported next to the headline (not part of it): backward, prob variant, DAF, and the
+    reference CUDA op on the same GPU when oracle/_ref travelled with the repo."""
+    import torch
+    from gaussianformer_b200.splat import LocalAggregator, LocalAggregatorProb
+    from gaussianformer_b200.synthetic import make_daf_inputs, make_splat_inputs
+    from gaussianformer_b200.ops import DeformableAggregationFunction as DAF
+    out = {}
+
+    def timeit(fn, reps=20, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    try:
+        m = LocalAggregator(**kw).to(dev)
+        m.validate = False
+        t = {k: v.to(dev) for k, v in inp0.items()}
+        for k in ("means", "opa", "sem", "cov"):
+            t[k].requires_grad_(True)
+        logits = m(t["pts"], t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
+        g = torch.randn_like(logits)
+        out["splat_bwd_ms"] = timeit(lambda: torch.autograd.grad(logits, [t["means"], t["opa"], t["sem"], t["cov"]], g,
+                                                                 retain_graph=True), reps=10)
+        kwp, inpp, _ = make_splat_inputs("prob_gs6400", seed=0, perturb=True)
+        mp = LocalAggregatorProb(**kwp).to(dev)
+        mp.validate = False
+        tp = {k: v.to(dev) for k, v in inpp.items()}
+        out["prob_gs6400_fwd_ms"] = timeit(lambda: mp(tp["pts"], tp["means"], tp["opa"], tp["sem"], tp["scales"], tp["cov"]), reps=10)
+        fms, loc, w = make_daf_inputs(seed=0)
+        feat, shape, start = DAF.feature_maps_format([f.to(dev) for f in fms])
+        feat = feat.contiguous()
+        loc, w = loc.to(dev), w.to(dev)
+        out["daf_fwd_ms"] = timeit(lambda: DAF.apply(feat, shape, start, loc, w), reps=10)
+        out["daf_fwd_alg_gbs"] = 4 * (feat.numel() + loc.numel() + w.numel() + loc.shape[1] * 128) / (out["daf_fwd_ms"] * 1e-3) / 1e9
+    except Exception as e:  # side figures must never sink the headline
+        out["extras_error"] = repr(e)
+    try:
+        from oracle import build_ref
+        if build_ref.available("gf_ref_localagg"):
+            mod = build_ref.load_ref("gf_ref_localagg")
+            t = {k: v[0].to(dev) for k, v in inp0.items()}
+            pc_min = torch.tensor(kw["pc_min"], device=dev)[None]
+
+            def ref_call():   # the reference's Python wrapper + native op (asserts included)
+                pi = ((t["pts"] - pc_min) / kw["grid_size"]).to(torch.int)
+                assert pi.min() >= 0
+                mi = ((t["means"] - pc_min) / kw["grid_size"]).to(torch.int)
+                assert mi.min() >= 0
+                radii = torch.ceil(t["scales"].max(dim=-1)[0] * kw["scale_multiplier"] / kw["grid_size"]).to(torch.int)
+                assert radii.min() >= 1
+                cov6 = t["cov"].flatten(1)[:, [0, 4, 8, 1, 5, 2]]
+                return mod.local_aggregate(t["pts"], pi, t["means"], mi, t["opa"], t["sem"], radii, cov6,
+                                           kw["H"], kw["W"], kw["D"])
+            out["ref_cuda_op"] = {"fwd_ms": timeit(ref_call, reps=10), "what": "reference localagg op call "
+                                  "(its Python prep + sort-based kernels) compiled for sm_100a, same GPU, same sample"}
+    except Exception as e:
+        out["ref_cuda_op"] = {"error": repr(e)}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -23,7 +23,7 @@ EXPORTS = (
     "gf_abi_version", "gf_last_error", "gf_splat_supported_classes",
     "gf_splat_forward_workspace_bytes", "gf_splat_backward_workspace_bytes",
     "gf_splat_forward", "gf_splat_backward", "gf_splat_read_flags",
-    "gf_daf_forward", "gf_daf_backward",
+    "gf_daf_forward", "gf_daf_backward", "gf_splat_set_render_events",
 )
 
 
@@ -84,6 +84,7 @@ def lib():
         L.gf_splat_backward.argtypes = [POINTER(SplatDesc), POINTER(SplatInputs), POINTER(SplatGrads), c_void_p,
                                         c_size_t, c_void_p]
         L.gf_splat_read_flags.argtypes = [c_void_p, c_void_p, POINTER(c_uint32)]
+        L.gf_splat_set_render_events.argtypes = [c_void_p, c_void_p]
         L.gf_daf_forward.argtypes = [POINTER(DafDesc)] + [c_void_p] * 7
         L.gf_daf_backward.argtypes = [POINTER(DafDesc)] + [c_void_p] * 10
         if L.gf_abi_version() != 1:

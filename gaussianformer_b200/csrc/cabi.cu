@@ -31,6 +31,7 @@ int launch_render(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_sp
 size_t backward_workspace_bytes(const gf_splat_desc &d);
 int launch_backward(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_splat_grads &gr, void *workspace,
                     int num_sms, cudaStream_t stream);
+extern thread_local cudaEvent_t g_ev_before, g_ev_after;
 extern const int kSupportedClasses[];
 extern const int kNumSupportedClasses;
 
@@ -40,6 +41,8 @@ int launch_daf_forward(const gf_daf_desc &d, const float *feat, const int32_t *s
 int launch_daf_backward(const gf_daf_desc &d, const float *feat, const int32_t *shape, const int32_t *start,
                         const float *loc, const float *weights, const float *grad_out, float *grad_feat,
                         float *grad_loc, float *grad_weights, int num_sms, cudaStream_t stream);
+
+thread_local cudaEvent_t g_ev_before = nullptr, g_ev_after = nullptr;
 
 static int num_sms_of_current_device(int *out) {
     static int cached[64];
@@ -95,6 +98,12 @@ extern "C" {
 int gf_abi_version(void) { return GF_ABI_VERSION; }
 
 const char *gf_last_error(void) { return g_err; }
+
+int gf_splat_set_render_events(void *before, void *after) {
+    g_ev_before = static_cast<cudaEvent_t>(before);
+    g_ev_after = static_cast<cudaEvent_t>(after);
+    return GF_OK;
+}
 
 int gf_splat_supported_classes(int32_t *out, int cap) {
     int n = 0;

@@ -20,6 +20,8 @@
 
 namespace gf {
 
+extern thread_local cudaEvent_t g_ev_before, g_ev_after;  // measurement hooks (cabi.cu)
+
 struct RenderParams {
     gf_splat_desc d;
     const float *pts;
@@ -377,16 +379,12 @@ template <int C, bool PROB>
 static int launch_render_t(const RenderParams &rp, bool tile_path, int num_sms, cudaStream_t stream) {
     if (tile_path) {
         const size_t smem = sizeof(RenderSmem<C>);
-        static bool configured = false;
-        if (!configured) {
-            GF_CUDA_TRY(cudaFuncSetAttribute(render_tile_kernel<C, PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem)));
-            configured = true;
-        }
         const int nbx = (rp.d.H + kBinX - 1) / kBinX;
         const int grid = nbx * rp.nby * rp.nzc;
+        if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_before, stream));
         render_tile_kernel<C, PROB><<<grid, kRenderThreads, smem, stream>>>(rp);
         GF_CUDA_TRY(cudaGetLastError());
+        if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_after, stream));
     }
     const long long want = (static_cast<long long>(rp.d.N) + 255) / 256;
     const int grid = static_cast<int>(want < 8ll * num_sms ? (want > 0 ? want : 1) : 8ll * num_sms);
@@ -395,8 +393,8 @@ static int launch_render_t(const RenderParams &rp, bool tile_path, int num_sms, 
     return GF_OK;
 }
 
-const int kSupportedClasses[] = {16, 17, 18, 19, 20};
-const int kNumSupportedClasses = sizeof(kSupportedClasses) / sizeof(int);
+extern const int kSupportedClasses[] = {16, 17, 18, 19, 20};
+extern const int kNumSupportedClasses = 5;
 
 int launch_render(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_splat_outputs &out,
                   const SplatWorkspace &ws, bool tile_path, int num_sms, cudaStream_t stream) {

@@ -215,8 +215,10 @@ int launch_prep(const gf_splat_desc &d, const gf_splat_inputs &in, const SplatWo
     pp.nsx = ws.nsx;
     pp.nsy = ws.nsy;
     pp.nwords = ws.nwords;
-    pack_mask_kernel<<<ws.pack_ctas, kPackThreads, 0, stream>>>(pp);
-    GF_CUDA_TRY(cudaGetLastError());
+    if (ws.pack_ctas > 0) {
+        pack_mask_kernel<<<ws.pack_ctas, kPackThreads, 0, stream>>>(pp);
+        GF_CUDA_TRY(cudaGetLastError());
+    }
     ListParams lp;
     lp.masks = ws.masks;
     lp.pack_flags = ws.pack_flags;

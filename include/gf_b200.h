@@ -148,6 +148,12 @@ int gf_splat_backward(const gf_splat_desc *desc, const gf_splat_inputs *in,
  * for the same conditions. */
 int gf_splat_read_flags(const void *workspace, gf_stream_t stream, uint32_t *host_flags);
 
+/* Measurement aid for bench.py's roofline line: when both events are non-NULL (cudaEvent_t created
+ * with timing enabled), every following gf_splat_forward on this thread records them on its stream
+ * immediately before / after the tile render kernel, so that kernel can be timed alone inside a
+ * normal run.  Pass NULLs to switch it off.  Not part of the reference boundary. */
+int gf_splat_set_render_events(void *before, void *after);
+
 /* out[B,P,C] is fully overwritten. */
 int gf_daf_forward(const gf_daf_desc *desc, const float *mc_ms_feat, const int32_t *spatial_shape,
                    const int32_t *scale_start_index, const float *sample_location,

@@ -48,7 +48,7 @@ struct RenderSmem {
 };
 
 template <int C, bool PROB>
-__global__ void __launch_bounds__(kRenderThreads, 4) render_tile_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kernel(const RenderParams p) {
     constexpr int REC = rec_floats(C);
     constexpr int CP = REC - kGeomFloats;
     extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -78,3 +78,21 @@ def grad_tolerance(ref):
     """Gradients are sums of up to ~1e5 signed terms: gate on the gradient's own scale."""
     ref = np.asarray(ref, np.float64)
     return 2e-4 * max(1.0, float(np.abs(ref).max()))
+
+
+def assert_argmax_parity(actual, expected, min_agree=0.9999):
+    """Occupancy prediction parity: the arg-max class must agree on >= 99.99 % of the voxels whose
+    decision is not a numerical tie (top-two margin of the reference above twice the tolerance);
+    a flip on a decided voxel is an error."""
+    actual = np.asarray(actual, np.float64)
+    expected = np.asarray(expected, np.float64)
+    am, ae = actual.argmax(1), expected.argmax(1)
+    rows = np.arange(expected.shape[0])
+    margin = expected[rows, ae] - expected[rows, am]
+    tol = 2 * (ATOL + RTOL * np.abs(expected[rows, ae]))
+    decided_flip = (am != ae) & (margin > tol)
+    assert not decided_flip.any(), f"{int(decided_flip.sum())} arg-max flips on decided voxels"
+    srt = np.sort(expected, axis=1)
+    decided = (srt[:, -1] - srt[:, -2]) > 2 * (ATOL + RTOL * np.abs(srt[:, -1]))
+    if decided.any():
+        assert (am == ae)[decided].mean() >= min_agree

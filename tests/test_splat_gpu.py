@@ -33,10 +33,7 @@ def test_base_forward_vs_oracle(cfg, seed, perturb, over):
     _, _, out = _run(kw, inp, variant)
     ref = h.oracle_forward(kw, inp, variant)
     h.assert_close(out.cpu().numpy(), ref["logits"], what="logits")
-    # argmax parity (voxels with any mass)
-    mass = np.abs(ref["logits"]).sum(1) > 0
-    agree = (out.argmax(1).cpu().numpy() == ref["logits"].argmax(1))[mass].mean() if mass.any() else 1.0
-    assert agree >= 0.9999
+    h.assert_argmax_parity(out.cpu().numpy(), ref["logits"])
 
 
 @pytest.mark.parametrize("cfg,seed,perturb,per_axis,over", [

@@ -105,8 +105,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return done != 0;
 }
+// Bounded spin: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
     }
 }
 // 1-D bulk async copy global -> shared through the TMA unit, completion counted on an mbarrier.

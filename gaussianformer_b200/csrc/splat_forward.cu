@@ -16,26 +16,13 @@
 //
 // render_points_kernel (generic path): one thread per point, arbitrary points (several per voxel,
 //   N != H*W*D), walks the supertile list with the exact box test.
-#include "common.cuh"
+#include <cstdlib>
+
+#include "splat_render.cuh"
 
 namespace gf {
 
 extern thread_local cudaEvent_t g_ev_before, g_ev_after;  // measurement hooks (cabi.cu)
-
-struct RenderParams {
-    gf_splat_desc d;
-    const float *pts;
-    const int32_t *points_int;
-    gf_splat_outputs out;
-    const float *records;
-    const PackedBox *boxes;
-    const int32_t *lists;
-    const int32_t *counts;
-    uint32_t *flags;
-    int st, nsy;     // supertile edge, supertiles along y
-    int nby;         // bins along y
-    int nzc;         // z chunks
-};
 
 template <int C>
 struct RenderSmem {
@@ -296,87 +283,29 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
 template <int C, bool PROB>
 __global__ void __launch_bounds__(256) render_points_kernel(const RenderParams p) {
     if (!(*reinterpret_cast<volatile uint32_t *>(p.flags) & GF_FLAG_GENERIC_PATH)) return;
-    constexpr int REC = rec_floats(C);
-    const int H = p.d.H, W = p.d.W, D = p.d.D;
-    for (long long n = blockIdx.x * 256ll + threadIdx.x; n < p.d.N; n += 256ll * gridDim.x) {
-        const float x = p.pts[3 * n], y = p.pts[3 * n + 1], z = p.pts[3 * n + 2];
-        int ix, iy, iz;
-        if (p.points_int) {
-            ix = p.points_int[3 * n]; iy = p.points_int[3 * n + 1]; iz = p.points_int[3 * n + 2];
-        } else {
-            ix = voxel_coord(x, p.d.pc_min[0], p.d.grid_size);
-            iy = voxel_coord(y, p.d.pc_min[1], p.d.grid_size);
-            iz = voxel_coord(z, p.d.pc_min[2], p.d.grid_size);
-        }
-        float acc[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = 0.f;
-        float zsum = 0.f, dens = 0.f, keep = 1.f;
-        const bool ok = ix >= 0 && ix < H && iy >= 0 && iy < W && iz >= 0 && iz < D;
-        if (!ok) {
-            atomicOr(p.flags, GF_FLAG_POINT_OUT_OF_GRID);
-        } else {
-            const int s = (ix / p.st) * p.nsy + (iy / p.st);
-            const int ncand = p.counts[s];
-            const int32_t *cand = p.lists + static_cast<size_t>(s) * p.d.G;
-            for (int i = 0; i < ncand; ++i) {
-                const int g = __ldg(cand + i);
-                const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p.boxes) + g);
-                const bool in = static_cast<uint32_t>(ix) >= (b.x & 0xffffu) && static_cast<uint32_t>(ix) <= (b.x >> 16) &&
-                                static_cast<uint32_t>(iy) >= (b.y & 0xffffu) && static_cast<uint32_t>(iy) <= (b.y >> 16) &&
-                                static_cast<uint32_t>(iz) >= (b.z & 0xffffu) && static_cast<uint32_t>(iz) <= (b.z >> 16) &&
-                                b.w == 0u;
-                if (!in) continue;
-                const float4 *r4 = reinterpret_cast<const float4 *>(p.records + static_cast<size_t>(g) * REC);
-                const float4 g0 = __ldg(r4), g1 = __ldg(r4 + 1), g2 = __ldg(r4 + 2);
-                const float dx = g0.x - x, dy = g0.y - y, dz = g0.z - z;
-                float t1 = g1.x * dx;
-                t1 = fmaf(g1.w, dy, t1);
-                t1 = fmaf(g2.y, dz, t1);
-                float t2 = g1.y * dy;
-                t2 = fmaf(g2.x, dz, t2);
-                float q = t1 * dx;
-                q = fmaf(t2, dy, q);
-                q = fmaf(g1.z * dz, dz, q);
-                const float E = ex2_approx(q);
-                const float w = g0.w * E;
-                if (PROB) {
-                    zsum += w;
-                    dens += E;
-                    keep *= (1.f - E);
-                }
-#pragma unroll
-                for (int c4 = 0; c4 < (REC - kGeomFloats) / 4; ++c4) {
-                    const float4 s4 = __ldg(r4 + 3 + c4);
-                    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (c4 * 4 + k < C) acc[c4 * 4 + k] = fmaf(sv[k], w, acc[c4 * 4 + k]);
-                }
-            }
-        }
-        if (PROB) {
-            if (zsum > 1e-9f) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) acc[c] = __fdiv_rn(acc[c], zsum);
-            } else {
-#pragma unroll
-                for (int c = 0; c < C; ++c) acc[c] = (c < C - 1) ? static_cast<float>(1.0 / (C - 1)) : 0.f;
-            }
-            p.out.bin_logits[n] = 1.f - keep;
-            p.out.density[n] = dens;
-            p.out.probability[n] = zsum;
-        }
-#pragma unroll
-        for (int c = 0; c < C; ++c) p.out.logits[n * C + c] = acc[c];
-    }
+    for (long long n = blockIdx.x * 256ll + threadIdx.x; n < p.d.N; n += 256ll * gridDim.x)
+        render_one_point<C, PROB>(p, n, p.pts[3 * n], p.pts[3 * n + 1], p.pts[3 * n + 2]);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+int launch_render_tc(const RenderParams &rp, cudaStream_t stream);  // splat_forward_tc.cu
+
+// GF_B200_RENDER=simt selects the first-generation SIMT tile kernel (kept for A/B measurements);
+// the default is the tcgen05 kernel, which also handles non-canonical points inline.
+static bool use_simt_render() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("GF_B200_RENDER");
+        cached = (e && e[0] == 's') ? 1 : 0;
+    }
+    return cached == 1;
+}
+
 template <int C, bool PROB>
 static int launch_render_t(const RenderParams &rp, bool tile_path, int num_sms, cudaStream_t stream) {
+    if (tile_path && !use_simt_render()) return launch_render_tc(rp, stream);
     if (tile_path) {
         const size_t smem = sizeof(RenderSmem<C>);
         const int nbx = (rp.d.H + kBinX - 1) / kBinX;

@@ -1,0 +1,424 @@
+// Splat render kernel, second generation: the per-voxel class accumulation as a dense contraction
+// on the 5th-generation tensor cores.
+//
+//   out[v, c] = sum_g  w[v, g] * s[g, c]      w[v,g] = k_g * exp2(q_g(x_v))  if voxel(v) in box(g) else 0
+//
+// (reference: FORWARD::renderCUDA, model/head/localagg/src/forward.cu:61-81; prob variant
+// model/head/localagg_prob/src/forward.cu:63-101.)  One 128-thread CTA owns a bin of 2x4 columns x
+// 16 z = 128 voxels, one voxel per thread = one row of the MMA.  Per batch of 16 listed Gaussians:
+//
+//   * records arrive by per-record 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx);
+//   * every thread evaluates its row of W (exact integer-box test, exp2 of the pre-scaled quadratic
+//     form) on the CUDA cores, splits each value into two TF32 terms (hi = top 19 bits, lo = w - hi)
+//     and stores them into the K-major, un-swizzled canonical UMMA layout in shared memory;
+//   * 16 threads build the class-matrix tile S (hi / lo) in the MN-major canonical layout;
+//   * one thread issues tcgen05.mma (kind::tf32, M=128, N=32, K=8): hi*hi + lo*hi + hi*lo, i.e. the
+//     "3xTF32" scheme, ~2^-21 relative error per product, accumulating in fp32 in TENSOR MEMORY;
+//     tcgen05.commit -> mbarrier tells the CTA when the operand tiles may be overwritten.
+//
+// The epilogue reads the 128x32 fp32 accumulator with tcgen05.ld (one row per thread) and writes
+// the C logits of each voxel.  For the prob variant an extra all-ones class column makes the tensor
+// core produce Z = sum_g P as well; density and the product of complements stay in registers.
+//
+// Points that are not in canonical voxel order are detected per thread (W row forced to zero) and
+// evaluated afterwards by render_one_point(), so no second kernel is needed when N == H*W*D.
+#include "splat_render.cuh"
+
+namespace gf {
+
+extern thread_local cudaEvent_t g_ev_before, g_ev_after;  // measurement hooks (cabi.cu)
+
+constexpr int kTcThreads = 128;
+constexpr int kTcK = 16;    // Gaussians per operand tile
+constexpr int kTcN = 32;    // MMA N (classes padded)
+constexpr int kTcSeg = 512; // list entries resolved per segment
+constexpr int kTcBinX = 2, kTcBinY = 4, kTcBinZ = 16;
+constexpr uint32_t kTmemCols = 32;
+
+// canonical UMMA layouts (byte offsets), cf. cute/atom/mma_traits_sm100.hpp "make_umma_desc":
+//   A  (K-major,  SWIZZLE_NONE): (m%8)*16 + (m/8)*SBO_A + (k/4)*LBO_A + (k%4)*4,  SBO_A = 128, LBO_A = 2048
+//   B  (MN-major, SWIZZLE_NONE): (n%4)*4 + (n/4)*SBO_B + (k%8)*16 + (k/8)*LBO_B,  LBO_B = 128, SBO_B = 256
+constexpr uint32_t kSboA = 128, kLboA = 2048, kLboB = 128, kSboB = (kTcK / 8) * 128;
+
+template <int C>
+struct TcSmem {
+    static constexpr int REC = rec_floats(C);
+    alignas(128) float rec[2][kTcK * REC];
+    alignas(128) uint32_t a_hi[128 * kTcK];
+    alignas(128) uint32_t a_lo[128 * kTcK];
+    alignas(128) uint32_t b_hi[kTcN * kTcK];
+    alignas(128) uint32_t b_lo[kTcN * kTcK];
+    alignas(8) uint2 list[kTcSeg];  // x: box relative to the bin (packed), y: Gaussian index
+    alignas(8) uint64_t bar_rec[2];
+    alignas(8) uint64_t bar_mma;
+    uint32_t tmem_base;
+    int warp_count[kTcThreads / 32];
+};
+
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;  // descriptor version of sm_100
+    return d;         // base offset 0, layout type 0 = SWIZZLE_NONE
+}
+
+// kind::tf32, D = F32, A = TF32 K-major, B = TF32 MN-major, N = 32, M = 128
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
+                                ((kTcN >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(kInstrDesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_load_32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int C, bool PROB>
+__global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderParams p) {
+    constexpr int REC = rec_floats(C);
+    constexpr int CP = REC - kGeomFloats;
+    static_assert(C + (PROB ? 1 : 0) <= kTcN, "class count exceeds the MMA N tile");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TcSmem<C> &sm = *reinterpret_cast<TcSmem<C> *>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = p.d.H, W = p.d.W, D = p.d.D;
+
+    // ---- my voxel: thread t <-> (lx, ly, lz) with z fastest, so a warp writes 32 contiguous rows ----
+    const int bin = blockIdx.x / p.nzc, zc = blockIdx.x % p.nzc;
+    const int bxi = bin / p.nby, byi = bin % p.nby;
+    const int binX0 = bxi * kTcBinX, binY0 = byi * kTcBinY, binZ0 = zc * kTcBinZ;
+    const int lx = tid >> 6, ly = (tid >> 4) & 3, lz = tid & 15;
+    const int X = binX0 + lx, Y = binY0 + ly, Z = binZ0 + lz;
+    const bool valid = X < H && Y < W && Z < D;
+    const long long n = (static_cast<long long>(X) * W + Y) * D + Z;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    bool canon = true;
+    if (valid) {
+        px = __ldg(p.pts + 3 * n); py = __ldg(p.pts + 3 * n + 1); pz = __ldg(p.pts + 3 * n + 2);
+        int ix, iy, iz;
+        if (p.points_int) {
+            ix = p.points_int[3 * n]; iy = p.points_int[3 * n + 1]; iz = p.points_int[3 * n + 2];
+        } else {
+            ix = voxel_coord(px, p.d.pc_min[0], p.d.grid_size);
+            iy = voxel_coord(py, p.d.pc_min[1], p.d.grid_size);
+            iz = voxel_coord(pz, p.d.pc_min[2], p.d.grid_size);
+        }
+        canon = ix == X && iy == Y && iz == Z;
+        if (!canon) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
+    }
+    const bool live = valid && canon;   // rows of W that may be non-zero
+
+    // ---- one-time setup: barriers, tensor memory, zeroed S tiles ---------------------------------
+    if (tid == 0) {
+        mbar_init(&sm.bar_rec[0], 1);
+        mbar_init(&sm.bar_rec[1], 1);
+        mbar_init(&sm.bar_mma, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
+                     "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = tid; i < kTcN * kTcK; i += kTcThreads) { sm.b_hi[i] = 0u; sm.b_lo[i] = 0u; }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    uint32_t rec_uses[2] = {0, 0};
+    uint32_t mma_commits = 0;
+    float dens = 0.f, keep = 1.f;
+
+    // byte offset of my row inside an A tile and of "my" Gaussian column inside a B tile
+    const uint32_t a_row = (tid & 7) * 16 + (tid >> 3) * kSboA;
+
+    // ---- candidates: the ascending list of this bin's supertile ------------------------------------
+    const int s = (binX0 / p.st) * p.nsy + (binY0 / p.st);
+    const int ncand = p.counts[s];
+    const int32_t *cand = p.lists + static_cast<size_t>(s) * p.d.G;
+    const uint32_t bX1 = min(binX0 + kTcBinX, H) - 1, bY1 = min(binY0 + kTcBinY, W) - 1, bZ1 = min(binZ0 + kTcBinZ, D) - 1;
+    // warp footprint inside the bin: x = warp/2, y in {2*(warp&1), 2*(warp&1)+1}, all 16 z
+    const uint32_t warp_x_bit = 1u << (warp >> 1), warp_y_bits = 3u << (2 + 2 * (warp & 1));
+
+    int cpos = 0;
+    while (cpos < ncand) {
+        // ======================= Phase A: ordered survivors of the box test ==========================
+        int nlist = 0;
+        while (cpos < ncand && nlist + kTcThreads <= kTcSeg) {
+            const int i = cpos + tid;
+            uint2 entry = make_uint2(0u, 0u);
+            bool hit = false;
+            if (i < ncand) {
+                const int g = __ldg(cand + i);
+                const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p.boxes) + g);
+                const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16,
+                               z0 = b.z & 0xffffu, z1 = b.z >> 16;
+                hit = x0 <= bX1 && x1 >= static_cast<uint32_t>(binX0) && y0 <= bY1 && y1 >= static_cast<uint32_t>(binY0) &&
+                      z0 <= bZ1 && z1 >= static_cast<uint32_t>(binZ0) && b.w == 0u;
+                // box relative to the bin: 2-bit x mask, 4-bit y mask, z start (4 bits), z span (4 bits)
+                const int rx0 = max(static_cast<int>(x0) - binX0, 0), rx1 = min(static_cast<int>(x1) - binX0, kTcBinX - 1);
+                const int ry0 = max(static_cast<int>(y0) - binY0, 0), ry1 = min(static_cast<int>(y1) - binY0, kTcBinY - 1);
+                const int rz0 = max(static_cast<int>(z0) - binZ0, 0), rz1 = min(static_cast<int>(z1) - binZ0, kTcBinZ - 1);
+                const uint32_t xm = ((2u << rx1) - 1u) & ~((1u << rx0) - 1u);
+                const uint32_t ym = ((2u << ry1) - 1u) & ~((1u << ry0) - 1u);
+                entry = make_uint2(xm | (ym << 2) | (static_cast<uint32_t>(rz0) << 6) | (static_cast<uint32_t>(rz1 - rz0) << 10),
+                                   static_cast<uint32_t>(g));
+            }
+            const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) sm.warp_count[warp] = __popc(ballot);
+            __syncthreads();
+            int off = nlist, total = 0;
+#pragma unroll
+            for (int k = 0; k < kTcThreads / 32; ++k) {
+                const int c = sm.warp_count[k];
+                if (k < warp) off += c;
+                total += c;
+            }
+            if (hit) sm.list[off + __popc(ballot & lanemask_lt())] = entry;
+            nlist += total;
+            cpos += kTcThreads;
+            __syncthreads();
+        }
+
+        // ======================= Phase B: W tiles on CUDA cores, contraction on tensor cores =========
+        const int nchunks = (nlist + kTcK - 1) / kTcK;
+        auto issue = [&](int k) {  // warp 0 stages the records of chunk k into ring slot k&1
+            const int slot = k & 1;
+            const int cnt = min(kTcK, nlist - k * kTcK);
+            if (lane == 0) mbar_expect_tx(&sm.bar_rec[slot], cnt * REC * 4);
+            __syncwarp();
+            if (lane < cnt) {
+                const uint32_t g = sm.list[k * kTcK + lane].y;
+                tma_load_1d(&sm.rec[slot][lane * REC], p.records + static_cast<size_t>(g) * REC, REC * 4, &sm.bar_rec[slot]);
+            }
+        };
+        if (warp == 0) {
+            if (nchunks > 0) issue(0);
+            if (nchunks > 1) issue(1);
+        }
+        for (int k = 0; k < nchunks; ++k) {
+            const int slot = k & 1;
+            const int cnt = min(kTcK, nlist - k * kTcK);
+            mbar_wait(&sm.bar_rec[slot], rec_uses[slot] & 1);
+            rec_uses[slot]++;
+
+            // ---- my row of W for these <= 16 Gaussians ------------------------------------------
+            float w[kTcK];
+#pragma unroll
+            for (int j = 0; j < kTcK; ++j) {
+                w[j] = 0.f;
+                if (j < cnt) {
+                    const uint32_t e = sm.list[k * kTcK + j].x;   // warp-uniform
+                    if ((e & warp_x_bit) && (e & warp_y_bits)) {
+                        const bool in = live && ((e >> lx) & (e >> (2 + ly)) & 1u) &&
+                                        static_cast<uint32_t>(lz - static_cast<int>((e >> 6) & 15u)) <= ((e >> 10) & 15u);
+                        if (in) {
+                            const float4 *r4 = reinterpret_cast<const float4 *>(&sm.rec[slot][j * REC]);
+                            const float4 g0 = r4[0], g1 = r4[1];
+                            const float2 g2 = *reinterpret_cast<const float2 *>(r4 + 2);
+                            const float dx = g0.x - px, dy = g0.y - py, dz = g0.z - pz;
+                            float t1 = g1.x * dx;
+                            t1 = fmaf(g1.w, dy, t1);
+                            t1 = fmaf(g2.y, dz, t1);
+                            float t2 = g1.y * dy;
+                            t2 = fmaf(g2.x, dz, t2);
+                            float q = t1 * dx;
+                            q = fmaf(t2, dy, q);
+                            q = fmaf(g1.z * dz, dz, q);
+                            const float E = ex2_approx(q);
+                            w[j] = g0.w * E;
+                            if (PROB) {
+                                dens += E;
+                                keep *= (1.f - E);
+                            }
+                        }
+                    }
+                }
+            }
+
+            // ---- the operand tiles are free once the previous batch's MMAs have completed -----------
+            if (mma_commits > 0) mbar_wait(&sm.bar_mma, (mma_commits - 1) & 1);
+            tc_fence_after();
+
+#pragma unroll
+            for (int kc = 0; kc < kTcK / 4; ++kc) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float v = w[kc * 4 + i];
+                    hi[i] = __float_as_uint(v) & 0xFFFFE000u;
+                    lo[i] = __float_as_uint(v - __uint_as_float(hi[i]));
+                }
+                *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.a_hi) + a_row + kc * kLboA) =
+                    make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.a_lo) + a_row + kc * kLboA) =
+                    make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            // ---- class tile: thread j < 16 owns Gaussian j of the batch ------------------------------
+            if (tid < kTcK) {
+                const uint32_t b_col = (tid & 7) * 16 + (tid >> 3) * kLboB;
+                const float4 *r4 = reinterpret_cast<const float4 *>(&sm.rec[slot][tid * REC]);
+#pragma unroll
+                for (int c4 = 0; c4 < kTcN / 4; ++c4) {
+                    float sv[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (tid < cnt) {
+                        if (c4 < CP / 4) {
+                            const float4 s4 = r4[3 + c4];
+                            sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (c4 * 4 + i >= C) sv[i] = 0.f;
+                            if (PROB && c4 * 4 + i == C) sv[i] = 1.f;   // all-ones column -> Z
+                        }
+                    }
+                    if (c4 * 4 < C + (PROB ? 1 : 0)) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            hi[i] = __float_as_uint(sv[i]) & 0xFFFFE000u;
+                            lo[i] = __float_as_uint(sv[i] - __uint_as_float(hi[i]));
+                        }
+                        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.b_hi) + b_col + c4 * kSboB) =
+                            make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.b_lo) + b_col + c4 * kSboB) =
+                            make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+            fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
+                const uint32_t b_hi = smem_u32(sm.b_hi), b_lo = smem_u32(sm.b_lo);
+#pragma unroll
+                for (int ks = 0; ks < kTcK / 8; ++ks) {
+                    const uint64_t dah = umma_smem_desc(a_hi + ks * 2 * kLboA, kLboA, kSboA);
+                    const uint64_t dal = umma_smem_desc(a_lo + ks * 2 * kLboA, kLboA, kSboA);
+                    const uint64_t dbh = umma_smem_desc(b_hi + ks * kLboB, kLboB, kSboB);
+                    const uint64_t dbl = umma_smem_desc(b_lo + ks * kLboB, kLboB, kSboB);
+                    umma_tf32(tmem, dah, dbh, (mma_commits > 0 || ks > 0) ? 1u : 0u);
+                    umma_tf32(tmem, dal, dbh, 1u);
+                    umma_tf32(tmem, dah, dbl, 1u);
+                }
+                umma_commit(&sm.bar_mma);
+            }
+            mma_commits++;
+            if (warp == 0 && k + 2 < nchunks) issue(k + 2);   // ring slot k&1 is free again
+        }
+    }
+
+    // ---- epilogue: accumulator row -> logits ------------------------------------------------------
+    float acc[32];
+    if (mma_commits > 0) {
+        mbar_wait(&sm.bar_mma, (mma_commits - 1) & 1);
+        tc_fence_after();
+        tmem_load_32(tmem + (static_cast<uint32_t>(warp * 32) << 16), acc);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    }
+    if (live) {
+        float *dst = p.out.logits + n * C;
+        if (PROB) {
+            const float zsum = acc[C];
+            if (zsum > 1e-9f) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = __fdiv_rn(acc[c], zsum);
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = (c < C - 1) ? static_cast<float>(1.0 / (C - 1)) : 0.f;
+            }
+            p.out.bin_logits[n] = 1.f - keep;
+            p.out.density[n] = dens;
+            p.out.probability[n] = zsum;
+        }
+        if ((C & 1) == 0) {
+#pragma unroll
+            for (int c = 0; c < C; c += 2) __stcs(reinterpret_cast<float2 *>(dst + c), make_float2(acc[c], acc[c + 1]));
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) dst[c] = acc[c];
+        }
+    } else if (valid) {
+        render_one_point<C, PROB>(p, n, px, py, pz);   // point n does not sit in voxel n
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int C, bool PROB>
+static int launch_render_tc_t(const RenderParams &rp_in, cudaStream_t stream) {
+    RenderParams rp = rp_in;
+    rp.nby = (rp.d.W + kTcBinY - 1) / kTcBinY;
+    rp.nzc = (rp.d.D + kTcBinZ - 1) / kTcBinZ;
+    const int nbx = (rp.d.H + kTcBinX - 1) / kTcBinX;
+    const long long grid = static_cast<long long>(nbx) * rp.nby * rp.nzc;
+    const size_t smem = sizeof(TcSmem<C>);
+    if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_before, stream));
+    render_tc_kernel<C, PROB><<<static_cast<unsigned>(grid), kTcThreads, smem, stream>>>(rp);
+    GF_CUDA_TRY(cudaGetLastError());
+    if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_after, stream));
+    return GF_OK;
+}
+
+int launch_render_tc(const RenderParams &rp, cudaStream_t stream) {
+    const bool prob = rp.d.variant == GF_SPLAT_PROB;
+#define GF_CASE(CC)                                                   \
+    case CC:                                                          \
+        return prob ? launch_render_tc_t<CC, true>(rp, stream)        \
+                    : launch_render_tc_t<CC, false>(rp, stream);
+    switch (rp.d.C) {
+        GF_CASE(16)
+        GF_CASE(17)
+        GF_CASE(18)
+        GF_CASE(19)
+        GF_CASE(20)
+        default:
+            set_error("splat: class count C=%d is not compiled in (supported: 16..20)", rp.d.C);
+            return GF_ERR_UNSUPPORTED;
+    }
+#undef GF_CASE
+}
+
+}  // namespace gf

@@ -11,7 +11,7 @@
 //   * every thread evaluates its row of W (exact integer-box test, exp2 of the pre-scaled quadratic
 //     form) on the CUDA cores, splits each value into two TF32 terms (hi = top 19 bits, lo = w - hi)
 //     and stores them into the K-major, un-swizzled canonical UMMA layout in shared memory;
-//   * 16 threads build the class-matrix tile S (hi / lo) in the MN-major canonical layout;
+//   * the class-matrix tile S (hi / lo) is written in the same K-major canonical layout;
 //   * one thread issues tcgen05.mma (kind::tf32, M=128, N=32, K=8): hi*hi + lo*hi + hi*lo, i.e. the
 //     "3xTF32" scheme, ~2^-21 relative error per product, accumulating in fp32 in TENSOR MEMORY;
 //     tcgen05.commit -> mbarrier tells the CTA when the operand tiles may be overwritten.
@@ -37,8 +37,11 @@ constexpr uint32_t kTmemCols = 32;
 
 // canonical UMMA layouts (byte offsets), cf. cute/atom/mma_traits_sm100.hpp "make_umma_desc":
 //   A  (K-major,  SWIZZLE_NONE): (m%8)*16 + (m/8)*SBO_A + (k/4)*LBO_A + (k%4)*4,  SBO_A = 128, LBO_A = 2048
-//   B  (MN-major, SWIZZLE_NONE): (n%4)*4 + (n/4)*SBO_B + (k%8)*16 + (k/8)*LBO_B,  LBO_B = 128, SBO_B = 256
-constexpr uint32_t kSboA = 128, kLboA = 2048, kLboB = 128, kSboB = (kTcK / 8) * 128;
+//   B  (K-major,  SWIZZLE_NONE): (n%8)*16 + (n/8)*SBO_B + (k/4)*LBO_B + (k%4)*4,  SBO_B = 128, LBO_B = 512
+// (LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = distance between 8-row
+// groups; verified on hardware by scratch/umma_test.cu.  MN-major operands are NOT usable with
+// kind::tf32 + SWIZZLE_NONE: the same probe returns all zeros for them.)
+constexpr uint32_t kSboA = 128, kLboA = 2048, kSboB = 128, kLboB = (kTcN / 8) * 128;
 
 template <int C>
 struct TcSmem {
@@ -64,8 +67,8 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
     return d;         // base offset 0, layout type 0 = SWIZZLE_NONE
 }
 
-// kind::tf32, D = F32, A = TF32 K-major, B = TF32 MN-major, N = 32, M = 128
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
+// kind::tf32, D = F32, A = TF32 K-major, B = TF32 K-major, N = 32, M = 128
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) |
                                 ((kTcN >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
@@ -92,12 +95,13 @@ __device__ __forceinline__ void tmem_load_32(uint32_t taddr, float (&v)[32]) {
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"   // same asm statement: the registers are not readable before the wait
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        : "r"(taddr)
+        : "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -285,35 +289,30 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
                 *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.a_lo) + a_row + kc * kLboA) =
                     make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            // ---- class tile: thread j < 16 owns Gaussian j of the batch ------------------------------
-            if (tid < kTcK) {
-                const uint32_t b_col = (tid & 7) * 16 + (tid >> 3) * kLboB;
-                const float4 *r4 = reinterpret_cast<const float4 *>(&sm.rec[slot][tid * REC]);
-#pragma unroll
-                for (int c4 = 0; c4 < kTcN / 4; ++c4) {
+            // ---- class tile S[k][n]: thread (k = tid % 16, n-group = tid / 16) moves 4 classes -------
+            {
+                const int kk = tid & (kTcK - 1), ng = tid >> 4;   // 8 groups of 4 classes
+                if (ng * 4 < C + (PROB ? 1 : 0)) {
                     float sv[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (tid < cnt) {
-                        if (c4 < CP / 4) {
-                            const float4 s4 = r4[3 + c4];
+                    if (kk < cnt) {
+                        if (ng < CP / 4) {
+                            const float4 s4 = reinterpret_cast<const float4 *>(&sm.rec[slot][kk * REC])[3 + ng];
                             sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            if (c4 * 4 + i >= C) sv[i] = 0.f;
-                            if (PROB && c4 * 4 + i == C) sv[i] = 1.f;   // all-ones column -> Z
+                            if (ng * 4 + i >= C) sv[i] = 0.f;
+                            if (PROB && ng * 4 + i == C) sv[i] = 1.f;   // all-ones column -> Z
                         }
                     }
-                    if (c4 * 4 < C + (PROB ? 1 : 0)) {
-                        uint32_t hi[4], lo[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            hi[i] = __float_as_uint(sv[i]) & 0xFFFFE000u;
-                            lo[i] = __float_as_uint(sv[i] - __uint_as_float(hi[i]));
-                        }
-                        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.b_hi) + b_col + c4 * kSboB) =
-                            make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.b_lo) + b_col + c4 * kSboB) =
-                            make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    for (int i = 0; i < 4; ++i) {
+                        const int nn = ng * 4 + i;
+                        const uint32_t off = (nn & 7) * 16 + (nn >> 3) * kSboB + (kk >> 2) * kLboB + (kk & 3) * 4;
+                        const uint32_t hi = __float_as_uint(sv[i]) & 0xFFFFE000u;
+                        const uint32_t lo = __float_as_uint(sv[i] - __uint_as_float(hi));
+                        *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sm.b_hi) + off) = hi;
+                        *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sm.b_lo) + off) = lo;
                     }
                 }
             }
@@ -328,8 +327,8 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
                 for (int ks = 0; ks < kTcK / 8; ++ks) {
                     const uint64_t dah = umma_smem_desc(a_hi + ks * 2 * kLboA, kLboA, kSboA);
                     const uint64_t dal = umma_smem_desc(a_lo + ks * 2 * kLboA, kLboA, kSboA);
-                    const uint64_t dbh = umma_smem_desc(b_hi + ks * kLboB, kLboB, kSboB);
-                    const uint64_t dbl = umma_smem_desc(b_lo + ks * kLboB, kLboB, kSboB);
+                    const uint64_t dbh = umma_smem_desc(b_hi + ks * 2 * kLboB, kLboB, kSboB);
+                    const uint64_t dbl = umma_smem_desc(b_lo + ks * 2 * kLboB, kLboB, kSboB);
                     umma_tf32(tmem, dah, dbh, (mma_commits > 0 || ks > 0) ? 1u : 0u);
                     umma_tf32(tmem, dal, dbh, 1u);
                     umma_tf32(tmem, dah, dbl, 1u);

@@ -4,8 +4,9 @@
 //   out[v, c] = sum_g  w[v, g] * s[g, c]      w[v,g] = k_g * exp2(q_g(x_v))  if voxel(v) in box(g) else 0
 //
 // (reference: FORWARD::renderCUDA, model/head/localagg/src/forward.cu:61-81; prob variant
-// model/head/localagg_prob/src/forward.cu:63-101.)  One 128-thread CTA owns a bin of 2x4 columns x
-// 16 z = 128 voxels, one voxel per thread = one row of the MMA.  Per batch of 16 listed Gaussians:
+// model/head/localagg_prob/src/forward.cu:63-101.)  One 128-thread CTA owns a bin of 4x4 columns x
+// 8 z = 128 voxels, one voxel per thread = one row of the MMA; a warp covers a compact 4x4x2 block
+// so that most of its lanes fall inside a Gaussian's box together.  Per batch of 16 listed Gaussians:
 //
 //   * records arrive by per-record 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx);
 //   * every thread evaluates its row of W (exact integer-box test, exp2 of the pre-scaled quadratic
@@ -32,7 +33,7 @@ constexpr int kTcThreads = 128;
 constexpr int kTcK = 16;    // Gaussians per operand tile
 constexpr int kTcN = 32;    // MMA N (classes padded)
 constexpr int kTcSeg = 512; // list entries resolved per segment
-constexpr int kTcBinX = 2, kTcBinY = 4, kTcBinZ = 16;
+constexpr int kTcBinX = 4, kTcBinY = 4, kTcBinZ = 8;
 constexpr uint32_t kTmemCols = 32;
 
 // canonical UMMA layouts (byte offsets), cf. cute/atom/mma_traits_sm100.hpp "make_umma_desc":
@@ -51,7 +52,7 @@ struct TcSmem {
     alignas(128) uint32_t a_lo[128 * kTcK];
     alignas(128) uint32_t b_hi[kTcN * kTcK];
     alignas(128) uint32_t b_lo[kTcN * kTcK];
-    alignas(8) uint2 list[kTcSeg];  // x: box relative to the bin (packed), y: Gaussian index
+    alignas(8) uint2 list[kTcSeg + kTcK];  // x: box relative to the bin (bit masks), y: Gaussian index
     alignas(8) uint64_t bar_rec[2];
     alignas(8) uint64_t bar_mma;
     uint32_t tmem_base;
@@ -117,11 +118,11 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.d.H, W = p.d.W, D = p.d.D;
 
-    // ---- my voxel: thread t <-> (lx, ly, lz) with z fastest, so a warp writes 32 contiguous rows ----
+    // ---- my voxel ------------------------------------------------------------------------------------
     const int bin = blockIdx.x / p.nzc, zc = blockIdx.x % p.nzc;
     const int bxi = bin / p.nby, byi = bin % p.nby;
     const int binX0 = bxi * kTcBinX, binY0 = byi * kTcBinY, binZ0 = zc * kTcBinZ;
-    const int lx = tid >> 6, ly = (tid >> 4) & 3, lz = tid & 15;
+    const int lx = lane >> 3, ly = (lane >> 1) & 3, lz = 2 * warp + (lane & 1);   // warp = 4 x 4 x 2 voxels
     const int X = binX0 + lx, Y = binY0 + ly, Z = binZ0 + lz;
     const bool valid = X < H && Y < W && Z < D;
     const long long n = (static_cast<long long>(X) * W + Y) * D + Z;
@@ -141,6 +142,9 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
         if (!canon) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
     }
     const bool live = valid && canon;   // rows of W that may be non-zero
+    // entry word of a listed Gaussian: x mask [0,4) | y mask [4,8) | z mask [8,16); I am inside its
+    // box iff all three of my bits are set (dead rows get a pattern no entry can match)
+    const uint32_t my_bits = live ? ((1u << lx) | (1u << (4 + ly)) | (1u << (8 + lz))) : 0xFFFFFFFFu;
 
     // ---- one-time setup: barriers, tensor memory, zeroed S tiles ---------------------------------
     if (tid == 0) {
@@ -172,8 +176,6 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
     const int ncand = p.counts[s];
     const int32_t *cand = p.lists + static_cast<size_t>(s) * p.d.G;
     const uint32_t bX1 = min(binX0 + kTcBinX, H) - 1, bY1 = min(binY0 + kTcBinY, W) - 1, bZ1 = min(binZ0 + kTcBinZ, D) - 1;
-    // warp footprint inside the bin: x = warp/2, y in {2*(warp&1), 2*(warp&1)+1}, all 16 z
-    const uint32_t warp_x_bit = 1u << (warp >> 1), warp_y_bits = 3u << (2 + 2 * (warp & 1));
 
     int cpos = 0;
     while (cpos < ncand) {
@@ -190,14 +192,14 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
                                z0 = b.z & 0xffffu, z1 = b.z >> 16;
                 hit = x0 <= bX1 && x1 >= static_cast<uint32_t>(binX0) && y0 <= bY1 && y1 >= static_cast<uint32_t>(binY0) &&
                       z0 <= bZ1 && z1 >= static_cast<uint32_t>(binZ0) && b.w == 0u;
-                // box relative to the bin: 2-bit x mask, 4-bit y mask, z start (4 bits), z span (4 bits)
+                // box relative to the bin as three bit masks
                 const int rx0 = max(static_cast<int>(x0) - binX0, 0), rx1 = min(static_cast<int>(x1) - binX0, kTcBinX - 1);
                 const int ry0 = max(static_cast<int>(y0) - binY0, 0), ry1 = min(static_cast<int>(y1) - binY0, kTcBinY - 1);
                 const int rz0 = max(static_cast<int>(z0) - binZ0, 0), rz1 = min(static_cast<int>(z1) - binZ0, kTcBinZ - 1);
                 const uint32_t xm = ((2u << rx1) - 1u) & ~((1u << rx0) - 1u);
                 const uint32_t ym = ((2u << ry1) - 1u) & ~((1u << ry0) - 1u);
-                entry = make_uint2(xm | (ym << 2) | (static_cast<uint32_t>(rz0) << 6) | (static_cast<uint32_t>(rz1 - rz0) << 10),
-                                   static_cast<uint32_t>(g));
+                const uint32_t zm = ((2u << rz1) - 1u) & ~((1u << rz0) - 1u);
+                entry = make_uint2(xm | (ym << 4) | (zm << 8), static_cast<uint32_t>(g));
             }
             const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
             if (lane == 0) sm.warp_count[warp] = __popc(ballot);
@@ -214,6 +216,10 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
             cpos += kTcThreads;
             __syncthreads();
         }
+
+        // pad the last batch with empty entries (mask 0 never matches), so Phase B needs no j < cnt test
+        if (tid < kTcK && nlist + tid < ((nlist + kTcK - 1) / kTcK) * kTcK) sm.list[nlist + tid] = make_uint2(0u, 0u);
+        __syncthreads();
 
         // ======================= Phase B: W tiles on CUDA cores, contraction on tensor cores =========
         const int nchunks = (nlist + kTcK - 1) / kTcK;
@@ -242,31 +248,25 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
 #pragma unroll
             for (int j = 0; j < kTcK; ++j) {
                 w[j] = 0.f;
-                if (j < cnt) {
-                    const uint32_t e = sm.list[k * kTcK + j].x;   // warp-uniform
-                    if ((e & warp_x_bit) && (e & warp_y_bits)) {
-                        const bool in = live && ((e >> lx) & (e >> (2 + ly)) & 1u) &&
-                                        static_cast<uint32_t>(lz - static_cast<int>((e >> 6) & 15u)) <= ((e >> 10) & 15u);
-                        if (in) {
-                            const float4 *r4 = reinterpret_cast<const float4 *>(&sm.rec[slot][j * REC]);
-                            const float4 g0 = r4[0], g1 = r4[1];
-                            const float2 g2 = *reinterpret_cast<const float2 *>(r4 + 2);
-                            const float dx = g0.x - px, dy = g0.y - py, dz = g0.z - pz;
-                            float t1 = g1.x * dx;
-                            t1 = fmaf(g1.w, dy, t1);
-                            t1 = fmaf(g2.y, dz, t1);
-                            float t2 = g1.y * dy;
-                            t2 = fmaf(g2.x, dz, t2);
-                            float q = t1 * dx;
-                            q = fmaf(t2, dy, q);
-                            q = fmaf(g1.z * dz, dz, q);
-                            const float E = ex2_approx(q);
-                            w[j] = g0.w * E;
-                            if (PROB) {
-                                dens += E;
-                                keep *= (1.f - E);
-                            }
-                        }
+                const uint32_t e = sm.list[k * kTcK + j].x;   // warp-uniform
+                if ((e & my_bits) == my_bits) {
+                    const float4 *r4 = reinterpret_cast<const float4 *>(&sm.rec[slot][j * REC]);
+                    const float4 g0 = r4[0], g1 = r4[1];
+                    const float2 g2 = *reinterpret_cast<const float2 *>(r4 + 2);
+                    const float dx = g0.x - px, dy = g0.y - py, dz = g0.z - pz;
+                    float t1 = g1.x * dx;
+                    t1 = fmaf(g1.w, dy, t1);
+                    t1 = fmaf(g2.y, dz, t1);
+                    float t2 = g1.y * dy;
+                    t2 = fmaf(g2.x, dz, t2);
+                    float q = t1 * dx;
+                    q = fmaf(t2, dy, q);
+                    q = fmaf(g1.z * dz, dz, q);
+                    const float E = ex2_approx(q);
+                    w[j] = g0.w * E;
+                    if (PROB) {
+                        dens += E;
+                        keep *= (1.f - E);
                     }
                 }
             }

@@ -11,6 +11,8 @@
 //                      integer box, and one ballot bit per supertile (16x16 columns) it overlaps.
 //   list_kernel        one CTA per supertile: popcount-scan of the mask words -> ascending
 //                      Gaussian index list (ascending order == the reference's stable sort order).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gf {
@@ -28,17 +30,43 @@ struct PackParams {
     int nwords;
 };
 
+constexpr int kMaskPass = 1024;  // supertiles resolved per shared-memory pass
+
 __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParams p) {
+    __shared__ uint32_t s_mask[kPackThreads / 32][kMaskPass];
+    __shared__ uint32_t s_err;
     const int g = blockIdx.x * kPackThreads + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool live = g < p.d.G;
+    if (threadIdx.x == 0) s_err = 0;
 
     uint32_t err = 0;
     int lo[3] = {1, 1, 1}, hi[3] = {0, 0, 0};
     bool empty = true;
     if (live) {
-        const float mu[3] = {p.in.means[3 * g], p.in.means[3 * g + 1], p.in.means[3 * g + 2]};
+        // ---- every load first (read-only path), then arithmetic, then stores ------------------------
+        const float mu[3] = {__ldg(p.in.means + 3 * g), __ldg(p.in.means + 3 * g + 1), __ldg(p.in.means + 3 * g + 2)};
+        float c6[6];
+        {
+            const float *cv = p.in.cov + static_cast<size_t>(g) * p.d.cov_stride;
+            if (p.d.cov_stride == 9) {  // flat entries [0,4,8,1,5,2] of the row-major 3x3 (__init__.py:143)
+                c6[0] = __ldg(cv); c6[1] = __ldg(cv + 4); c6[2] = __ldg(cv + 8);
+                c6[3] = __ldg(cv + 1); c6[4] = __ldg(cv + 5); c6[5] = __ldg(cv + 2);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) c6[i] = __ldg(cv + i);
+            }
+        }
+        float amp = __ldg(p.in.opacities + g);
+        const int nq = (p.rec - kGeomFloats) / 4;   // <= 5 for C <= 20
+        float semv[20];
+        {
+            const float *sem = p.in.semantics + static_cast<size_t>(g) * p.d.C;
+#pragma unroll
+            for (int i = 0; i < 20; ++i) semv[i] = (i < p.d.C) ? __ldg(sem + i) : 0.f;
+        }
         empty = gaussian_box(p.d, p.in, g, mu, lo, hi, err);
+
         PackedBox b;
         b.x = empty ? 1u : (static_cast<uint32_t>(lo[0]) | static_cast<uint32_t>(hi[0]) << 16);
         b.y = empty ? 1u : (static_cast<uint32_t>(lo[1]) | static_cast<uint32_t>(hi[1]) << 16);
@@ -46,11 +74,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
         b.empty = empty ? 1u : 0u;
         p.boxes[g] = b;
 
-        // ---- record -------------------------------------------------------------------------
-        float c6[6];
-        load_cov6(p.d, p.in.cov, g, c6);
         const float a_ = c6[0], b_ = c6[1], c_ = c6[2], d_ = c6[3], e_ = c6[4], f_ = c6[5];
-        float amp = p.in.opacities[g];
         if (p.d.variant == GF_SPLAT_PROB) {
             // (2*pi)^-1.5 * sqrt(det) * opacity   (localagg_prob/src/forward.cu:77-78)
             const float det = a_ * b_ * c_ + 2.f * d_ * e_ * f_ - a_ * e_ * e_ - b_ * f_ * f_ - c_ * d_ * d_;
@@ -60,42 +84,34 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
         rec[0] = make_float4(mu[0], mu[1], mu[2], amp);
         rec[1] = make_float4(-0.5f * kLog2e * a_, -0.5f * kLog2e * b_, -0.5f * kLog2e * c_, -kLog2e * d_);
         rec[2] = make_float4(-kLog2e * e_, -kLog2e * f_, 0.f, 0.f);
-        const float *sem = p.in.semantics + static_cast<size_t>(g) * p.d.C;
-        const int nq = (p.rec - kGeomFloats) / 4;
-        for (int q = 0; q < nq; ++q) {
-            float v[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = (4 * q + i < p.d.C) ? sem[4 * q + i] : 0.f;
-            rec[3 + q] = make_float4(v[0], v[1], v[2], v[3]);
+        for (int q = 0; q < 5; ++q)
+            if (q < nq) rec[3 + q] = make_float4(semv[4 * q], semv[4 * q + 1], semv[4 * q + 2], semv[4 * q + 3]);
+    }
+
+    // ---- supertile masks: per-warp words assembled in shared memory, stored by all lanes ------------
+    const int sx0 = empty ? 1 : lo[0] / p.st, sx1 = empty ? 0 : hi[0] / p.st;
+    const int sy0 = empty ? 1 : lo[1] / p.st, sy1 = empty ? 0 : hi[1] / p.st;
+    const int word = g >> 5;          // warp-uniform
+    const int nsuper = p.nsx * p.nsy;
+    if (word < p.nwords) {
+        for (int base = 0; base < nsuper; base += kMaskPass) {
+            const int npass = min(kMaskPass, nsuper - base);
+            for (int i = lane; i < npass; i += 32) s_mask[warp][i] = 0u;
+            __syncwarp();
+            for (int sx = sx0; sx <= sx1; ++sx)
+                for (int sy = sy0; sy <= sy1; ++sy) {
+                    const int s = sx * p.nsy + sy - base;
+                    if (s >= 0 && s < npass) atomicOr(&s_mask[warp][s], 1u << lane);
+                }
+            __syncwarp();
+            for (int i = lane; i < npass; i += 32)
+                p.masks[static_cast<size_t>(base + i) * p.nwords + word] = s_mask[warp][i];
+            __syncwarp();
         }
     }
 
-    // ---- supertile masks: one ballot per supertile, every word is written (no memset needed) ----
-    const int sx0 = empty ? 1 : lo[0] / p.st, sx1 = empty ? 0 : hi[0] / p.st;
-    const int sy0 = empty ? 1 : lo[1] / p.st, sy1 = empty ? 0 : hi[1] / p.st;
-    // warp-wide union of touched supertiles (uniform), so untouched ones cost one store
-    int ux0 = empty ? 0x7fffffff : sx0, ux1 = empty ? -1 : sx1, uy0 = empty ? 0x7fffffff : sy0, uy1 = empty ? -1 : sy1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ux0 = min(ux0, __shfl_xor_sync(0xffffffffu, ux0, o));
-        ux1 = max(ux1, __shfl_xor_sync(0xffffffffu, ux1, o));
-        uy0 = min(uy0, __shfl_xor_sync(0xffffffffu, uy0, o));
-        uy1 = max(uy1, __shfl_xor_sync(0xffffffffu, uy1, o));
-    }
-    const int word = g >> 5;
-    if (word < p.nwords) {
-        for (int sx = 0; sx < p.nsx; ++sx)
-            for (int sy = 0; sy < p.nsy; ++sy) {
-                uint32_t bits = 0;
-                if (sx >= ux0 && sx <= ux1 && sy >= uy0 && sy <= uy1)
-                    bits = __ballot_sync(0xffffffffu, !empty && sx >= sx0 && sx <= sx1 && sy >= sy0 && sy <= sy1);
-                if (lane == 0) p.masks[static_cast<size_t>(sx * p.nsy + sy) * p.nwords + word] = bits;
-            }
-    }
-
     // ---- per-CTA error bits (plain store; list_kernel folds them into the status word) ----------
-    __shared__ uint32_t s_err;
-    if (threadIdx.x == 0) s_err = 0;
     __syncthreads();
     if (err) atomicOr(&s_err, err);
     __syncthreads();
@@ -170,7 +186,14 @@ __global__ void __launch_bounds__(kListThreads) list_kernel(const ListParams p) 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int plan_forward_workspace(const gf_splat_desc &d, void *base, SplatWorkspace *ws) {
-    int st = 16;
+    // supertile edge in columns: a multiple of both render bin edges (8 and 4); GF_B200_ST overrides
+    static int st_default = 0;
+    if (st_default == 0) {
+        const char *e = getenv("GF_B200_ST");
+        const int v = e ? atoi(e) : 16;
+        st_default = (v >= 8 && (v & (v - 1)) == 0) ? v : 16;
+    }
+    int st = st_default;
     const size_t budget = size_t(512) << 20;
     while (true) {
         const size_t ns = size_t((d.H + st - 1) / st) * size_t((d.W + st - 1) / st);

@@ -41,7 +41,8 @@ constexpr int kSeg = 512;       // bin-list entries resolved per segment
 constexpr int kGeomFloats = 12; // mu(3) k(1) c6(6) pad(2)
 
 __host__ __device__ constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
-__host__ __device__ constexpr int rec_floats(int C) { return kGeomFloats + round_up(C, 4); }
+// one record = geometry + class vector, padded to a whole number of 128-byte lines
+__host__ __device__ constexpr int rec_floats(int C) { return round_up(kGeomFloats + round_up(C, 4), 32); }
 
 // Integer box of one Gaussian, inclusive bounds packed lo | hi << 16 per axis; w = 1 when the
 // clipped box is empty.  (reference: getRect, model/head/localagg/src/auxiliary.h:8-20)

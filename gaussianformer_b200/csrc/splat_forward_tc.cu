@@ -54,9 +54,11 @@ struct TcSmem {
     alignas(128) uint32_t b_lo[kTcN * kTcK];
     alignas(8) uint2 list[kTcSeg + kTcK];  // x: box relative to the bin (bit masks), y: Gaussian index
     alignas(8) uint64_t bar_rec[2];
-    alignas(8) uint64_t bar_mma;
+    alignas(8) uint64_t bar_full;
+    alignas(8) uint64_t bar_free;
     uint32_t tmem_base;
     int warp_count[kTcThreads / 32];
+    int nlist, last;
 };
 
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -107,24 +109,46 @@ __device__ __forceinline__ void tmem_load_32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- small PTX helpers of the warp-specialised pipeline ---------------------------------------------
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// the mbarrier receives one arrival from this thread when all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTcThreads) : "memory"); }
+
+// Thread roles: threads 0..127 (4 warps) own one voxel each and produce the operand tiles; warp 4 is
+// the control warp: it owns tensor memory and its lane 0 issues the MMAs, so no compute warp ever
+// serialises the others behind descriptor arithmetic.  All hand-offs inside the batch loop are
+// mbarriers (no CTA-wide barrier):
+//   rec_full[2]   records of a batch have landed (cp.async arrivals of the 128 compute threads)
+//   tiles_full    all compute threads have written their part of the A / B tiles
+//   tiles_free    the MMAs that read those tiles have completed (tcgen05.commit)
 template <int C, bool PROB>
-__global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const RenderParams p) {
     constexpr int REC = rec_floats(C);
     constexpr int CP = REC - kGeomFloats;
+    static_assert(REC == 32, "one record = 128 bytes = 8 cp.async chunks");
     static_assert(C + (PROB ? 1 : 0) <= kTcN, "class count exceeds the MMA N tile");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TcSmem<C> &sm = *reinterpret_cast<TcSmem<C> *>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_compute = warp < kTcThreads / 32;
     const int H = p.d.H, W = p.d.W, D = p.d.D;
 
-    // ---- my voxel ------------------------------------------------------------------------------------
+    // ---- my voxel (compute threads) ---------------------------------------------------------------------
     const int bin = blockIdx.x / p.nzc, zc = blockIdx.x % p.nzc;
     const int bxi = bin / p.nby, byi = bin % p.nby;
     const int binX0 = bxi * kTcBinX, binY0 = byi * kTcBinY, binZ0 = zc * kTcBinZ;
-    const int lx = lane >> 3, ly = (lane >> 1) & 3, lz = 2 * warp + (lane & 1);   // warp = 4 x 4 x 2 voxels
+    const int lx = lane >> 3, ly = (lane >> 1) & 3, lz = 2 * (warp & 3) + (lane & 1);   // warp = 4 x 4 x 2 voxels
     const int X = binX0 + lx, Y = binY0 + ly, Z = binZ0 + lz;
-    const bool valid = X < H && Y < W && Z < D;
+    const bool valid = is_compute && X < H && Y < W && Z < D;
     const long long n = (static_cast<long long>(X) * W + Y) * D + Z;
     float px = 0.f, py = 0.f, pz = 0.f;
     bool canon = true;
@@ -148,28 +172,28 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
 
     // ---- one-time setup: barriers, tensor memory, zeroed S tiles ---------------------------------
     if (tid == 0) {
-        mbar_init(&sm.bar_rec[0], 1);
-        mbar_init(&sm.bar_rec[1], 1);
-        mbar_init(&sm.bar_mma, 1);
+        mbar_init(&sm.bar_rec[0], kTcThreads);
+        mbar_init(&sm.bar_rec[1], kTcThreads);
+        mbar_init(&sm.bar_full, kTcThreads);
+        mbar_init(&sm.bar_free, 1);
         mbar_fence_init();
     }
-    if (warp == 0) {
+    if (!is_compute) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
                      "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = tid; i < kTcN * kTcK; i += kTcThreads) { sm.b_hi[i] = 0u; sm.b_lo[i] = 0u; }
+    for (int i = tid; i < kTcN * kTcK; i += kTcThreads + 32) { sm.b_hi[i] = 0u; sm.b_lo[i] = 0u; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
 
-    uint32_t rec_uses[2] = {0, 0};
-    uint32_t mma_commits = 0;
     float dens = 0.f, keep = 1.f;
+    uint32_t gc = 0;   // batches processed so far by this CTA (drives every ring slot / parity)
 
-    // byte offset of my row inside an A tile and of "my" Gaussian column inside a B tile
-    const uint32_t a_row = (tid & 7) * 16 + (tid >> 3) * kSboA;
+    // byte offset of my row inside an A tile
+    const uint32_t a_row = (tid & 7) * 16 + ((tid & 127) >> 3) * kSboA;
 
     // ---- candidates: the ascending list of this bin's supertile ------------------------------------
     const int s = (binX0 / p.st) * p.nsy + (binY0 / p.st);
@@ -178,78 +202,106 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
     const uint32_t bX1 = min(binX0 + kTcBinX, H) - 1, bY1 = min(binY0 + kTcBinY, W) - 1, bZ1 = min(binZ0 + kTcBinZ, D) - 1;
 
     int cpos = 0;
-    while (cpos < ncand) {
-        // ======================= Phase A: ordered survivors of the box test ==========================
-        int nlist = 0;
-        while (cpos < ncand && nlist + kTcThreads <= kTcSeg) {
-            const int i = cpos + tid;
-            uint2 entry = make_uint2(0u, 0u);
-            bool hit = false;
-            if (i < ncand) {
-                const int g = __ldg(cand + i);
-                const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p.boxes) + g);
-                const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16,
-                               z0 = b.z & 0xffffu, z1 = b.z >> 16;
-                hit = x0 <= bX1 && x1 >= static_cast<uint32_t>(binX0) && y0 <= bY1 && y1 >= static_cast<uint32_t>(binY0) &&
-                      z0 <= bZ1 && z1 >= static_cast<uint32_t>(binZ0) && b.w == 0u;
-                // box relative to the bin as three bit masks
-                const int rx0 = max(static_cast<int>(x0) - binX0, 0), rx1 = min(static_cast<int>(x1) - binX0, kTcBinX - 1);
-                const int ry0 = max(static_cast<int>(y0) - binY0, 0), ry1 = min(static_cast<int>(y1) - binY0, kTcBinY - 1);
-                const int rz0 = max(static_cast<int>(z0) - binZ0, 0), rz1 = min(static_cast<int>(z1) - binZ0, kTcBinZ - 1);
-                const uint32_t xm = ((2u << rx1) - 1u) & ~((1u << rx0) - 1u);
-                const uint32_t ym = ((2u << ry1) - 1u) & ~((1u << ry0) - 1u);
-                const uint32_t zm = ((2u << rz1) - 1u) & ~((1u << rz0) - 1u);
-                entry = make_uint2(xm | (ym << 4) | (zm << 8), static_cast<uint32_t>(g));
-            }
-            const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) sm.warp_count[warp] = __popc(ballot);
-            __syncthreads();
-            int off = nlist, total = 0;
+    bool last;
+    do {
+        // ======================= Phase A (compute warps): ordered survivors of the box test ===========
+        if (is_compute) {
+            int nlist = 0;
+            while (cpos < ncand && nlist + kTcThreads <= kTcSeg) {
+                const int i = cpos + tid;
+                uint2 entry = make_uint2(0u, 0u);
+                bool hit = false;
+                if (i < ncand) {
+                    const int g = __ldg(cand + i);
+                    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p.boxes) + g);
+                    const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16,
+                                   z0 = b.z & 0xffffu, z1 = b.z >> 16;
+                    hit = x0 <= bX1 && x1 >= static_cast<uint32_t>(binX0) && y0 <= bY1 && y1 >= static_cast<uint32_t>(binY0) &&
+                          z0 <= bZ1 && z1 >= static_cast<uint32_t>(binZ0) && b.w == 0u;
+                    // box relative to the bin as three bit masks
+                    const int rx0 = max(static_cast<int>(x0) - binX0, 0), rx1 = min(static_cast<int>(x1) - binX0, kTcBinX - 1);
+                    const int ry0 = max(static_cast<int>(y0) - binY0, 0), ry1 = min(static_cast<int>(y1) - binY0, kTcBinY - 1);
+                    const int rz0 = max(static_cast<int>(z0) - binZ0, 0), rz1 = min(static_cast<int>(z1) - binZ0, kTcBinZ - 1);
+                    const uint32_t xm = ((2u << rx1) - 1u) & ~((1u << rx0) - 1u);
+                    const uint32_t ym = ((2u << ry1) - 1u) & ~((1u << ry0) - 1u);
+                    const uint32_t zm = ((2u << rz1) - 1u) & ~((1u << rz0) - 1u);
+                    entry = make_uint2(xm | (ym << 4) | (zm << 8), static_cast<uint32_t>(g));
+                }
+                const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) sm.warp_count[warp] = __popc(ballot);
+                compute_warps_sync();
+                int off = nlist, total = 0;
 #pragma unroll
-            for (int k = 0; k < kTcThreads / 32; ++k) {
-                const int c = sm.warp_count[k];
-                if (k < warp) off += c;
-                total += c;
+                for (int k = 0; k < kTcThreads / 32; ++k) {
+                    const int c = sm.warp_count[k];
+                    if (k < warp) off += c;
+                    total += c;
+                }
+                if (hit) sm.list[off + __popc(ballot & lanemask_lt())] = entry;
+                nlist += total;
+                cpos += kTcThreads;
+                compute_warps_sync();
             }
-            if (hit) sm.list[off + __popc(ballot & lanemask_lt())] = entry;
-            nlist += total;
-            cpos += kTcThreads;
-            __syncthreads();
+            // pad the last batch with empty entries (mask 0 never matches)
+            if (tid < kTcK && nlist + tid < ((nlist + kTcK - 1) / kTcK) * kTcK) sm.list[nlist + tid] = make_uint2(0u, 0u);
+            if (tid == 0) {
+                sm.nlist = nlist;
+                sm.last = cpos >= ncand ? 1 : 0;
+            }
         }
-
-        // pad the last batch with empty entries (mask 0 never matches), so Phase B needs no j < cnt test
-        if (tid < kTcK && nlist + tid < ((nlist + kTcK - 1) / kTcK) * kTcK) sm.list[nlist + tid] = make_uint2(0u, 0u);
         __syncthreads();
-
-        // ======================= Phase B: W tiles on CUDA cores, contraction on tensor cores =========
+        const int nlist = sm.nlist;
+        last = sm.last != 0;
         const int nchunks = (nlist + kTcK - 1) / kTcK;
-        auto issue = [&](int k) {  // warp 0 stages the records of chunk k into ring slot k&1
-            const int slot = k & 1;
-            const int cnt = min(kTcK, nlist - k * kTcK);
-            if (lane == 0) mbar_expect_tx(&sm.bar_rec[slot], cnt * REC * 4);
-            __syncwarp();
-            if (lane < cnt) {
-                const uint32_t g = sm.list[k * kTcK + lane].y;
-                tma_load_1d(&sm.rec[slot][lane * REC], p.records + static_cast<size_t>(g) * REC, REC * 4, &sm.bar_rec[slot]);
-            }
-        };
-        if (warp == 0) {
-            if (nchunks > 0) issue(0);
-            if (nchunks > 1) issue(1);
-        }
-        for (int k = 0; k < nchunks; ++k) {
-            const int slot = k & 1;
-            const int cnt = min(kTcK, nlist - k * kTcK);
-            mbar_wait(&sm.bar_rec[slot], rec_uses[slot] & 1);
-            rec_uses[slot]++;
 
-            // ---- my row of W for these <= 16 Gaussians ------------------------------------------
-            float w[kTcK];
+        if (!is_compute) {
+            // ======================= control warp: tensor-core issue ====================================
+            if (lane == 0) {
+                const uint32_t a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
+                const uint32_t b_hi = smem_u32(sm.b_hi), b_lo = smem_u32(sm.b_lo);
+                uint64_t dah[kTcK / 8], dal[kTcK / 8], dbh[kTcK / 8], dbl[kTcK / 8];
 #pragma unroll
-            for (int j = 0; j < kTcK; ++j) {
-                w[j] = 0.f;
-                const uint32_t e = sm.list[k * kTcK + j].x;   // warp-uniform
-                if ((e & my_bits) == my_bits) {
+                for (int ks = 0; ks < kTcK / 8; ++ks) {
+                    dah[ks] = umma_smem_desc(a_hi + ks * 2 * kLboA, kLboA, kSboA);
+                    dal[ks] = umma_smem_desc(a_lo + ks * 2 * kLboA, kLboA, kSboA);
+                    dbh[ks] = umma_smem_desc(b_hi + ks * 2 * kLboB, kLboB, kSboB);
+                    dbl[ks] = umma_smem_desc(b_lo + ks * 2 * kLboB, kLboB, kSboB);
+                }
+                for (int k = 0; k < nchunks; ++k, ++gc) {
+                    mbar_wait(&sm.bar_full, gc & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < kTcK / 8; ++ks) {
+                        umma_tf32(tmem, dah[ks], dbh[ks], (gc > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(tmem, dal[ks], dbh[ks], 1u);
+                        umma_tf32(tmem, dah[ks], dbl[ks], 1u);
+                    }
+                    umma_commit(&sm.bar_free);
+                }
+            }
+        } else {
+            // ======================= compute warps: W / S tiles ===========================================
+            auto load_records = [&](int k, uint32_t g_index) {   // batch k of this segment -> ring slot g_index & 1
+                const int slot = g_index & 1;
+                const int row = tid >> 3;                          // 16 records x 8 chunks of 16 bytes
+                if (k * kTcK + row < nlist) {
+                    const uint32_t g = sm.list[k * kTcK + row].y;
+                    cp_async_16(&sm.rec[slot][row * REC + (tid & 7) * 4], p.records + static_cast<size_t>(g) * REC + (tid & 7) * 4);
+                }
+                cp_async_arrive(&sm.bar_rec[slot]);
+            };
+            if (nchunks > 0) load_records(0, gc);
+            if (nchunks > 1) load_records(1, gc + 1);
+            for (int k = 0; k < nchunks; ++k, ++gc) {
+                const int slot = gc & 1;
+                const int cnt = min(kTcK, nlist - k * kTcK);
+                mbar_wait(&sm.bar_rec[slot], (gc >> 1) & 1);
+
+                // ---- my row of W for these 16 Gaussians: branch-free so the 16 evaluations overlap --------
+                float w[kTcK];
+#pragma unroll
+                for (int j = 0; j < kTcK; ++j) {
+                    const uint32_t e = sm.list[k * kTcK + j].x;   // warp-uniform
                     const float4 *r4 = reinterpret_cast<const float4 *>(&sm.rec[slot][j * REC]);
                     const float4 g0 = r4[0], g1 = r4[1];
                     const float2 g2 = *reinterpret_cast<const float2 *>(r4 + 2);
@@ -262,49 +314,48 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
                     float q = t1 * dx;
                     q = fmaf(t2, dy, q);
                     q = fmaf(g1.z * dz, dz, q);
-                    const float E = ex2_approx(q);
-                    w[j] = g0.w * E;
+                    const bool in = (e & my_bits) == my_bits;
+                    const float Eraw = ex2_approx(q);
+                    const float E = in ? Eraw : 0.f;          // select AFTER the arithmetic: padded slots hold
+                    w[j] = in ? g0.w * Eraw : 0.f;            // stale bytes and must never leak a NaN into W
                     if (PROB) {
                         dens += E;
                         keep *= (1.f - E);
                     }
                 }
-            }
-
-            // ---- the operand tiles are free once the previous batch's MMAs have completed -----------
-            if (mma_commits > 0) mbar_wait(&sm.bar_mma, (mma_commits - 1) & 1);
-            tc_fence_after();
-
-#pragma unroll
-            for (int kc = 0; kc < kTcK / 4; ++kc) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float v = w[kc * 4 + i];
-                    hi[i] = __float_as_uint(v) & 0xFFFFE000u;
-                    lo[i] = __float_as_uint(v - __uint_as_float(hi[i]));
-                }
-                *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.a_hi) + a_row + kc * kLboA) =
-                    make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.a_lo) + a_row + kc * kLboA) =
-                    make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            // ---- class tile S[k][n]: thread (k = tid % 16, n-group = tid / 16) moves 4 classes -------
-            {
+                // ---- my 4 classes of Gaussian kk for the S tile ---------------------------------------------
                 const int kk = tid & (kTcK - 1), ng = tid >> 4;   // 8 groups of 4 classes
-                if (ng * 4 < C + (PROB ? 1 : 0)) {
-                    float sv[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (kk < cnt) {
-                        if (ng < CP / 4) {
-                            const float4 s4 = reinterpret_cast<const float4 *>(&sm.rec[slot][kk * REC])[3 + ng];
-                            sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            if (ng * 4 + i >= C) sv[i] = 0.f;
-                            if (PROB && ng * 4 + i == C) sv[i] = 1.f;   // all-ones column -> Z
-                        }
+                float sv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (ng * 4 < C + (PROB ? 1 : 0) && kk < cnt) {
+                    if (ng < CP / 4) {
+                        const float4 s4 = reinterpret_cast<const float4 *>(&sm.rec[slot][kk * REC])[3 + ng];
+                        sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
                     }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (ng * 4 + i >= C) sv[i] = 0.f;
+                        if (PROB && ng * 4 + i == C) sv[i] = 1.f;   // all-ones column -> Z
+                    }
+                }
+
+                // ---- the operand tiles are free once the previous batch's MMAs have completed -----------
+                if (gc > 0) mbar_wait(&sm.bar_free, (gc - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kc = 0; kc < kTcK / 4; ++kc) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float v = w[kc * 4 + i];
+                        hi[i] = __float_as_uint(v) & 0xFFFFE000u;
+                        lo[i] = __float_as_uint(v - __uint_as_float(hi[i]));
+                    }
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.a_hi) + a_row + kc * kLboA) =
+                        make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.a_lo) + a_row + kc * kLboA) =
+                        make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                if (ng * 4 < C + (PROB ? 1 : 0)) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int nn = ng * 4 + i;
@@ -315,70 +366,62 @@ __global__ void __launch_bounds__(kTcThreads, 8) render_tc_kernel(const RenderPa
                         *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sm.b_lo) + off) = lo;
                     }
                 }
-            }
-            fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
-                const uint32_t b_hi = smem_u32(sm.b_hi), b_lo = smem_u32(sm.b_lo);
-#pragma unroll
-                for (int ks = 0; ks < kTcK / 8; ++ks) {
-                    const uint64_t dah = umma_smem_desc(a_hi + ks * 2 * kLboA, kLboA, kSboA);
-                    const uint64_t dal = umma_smem_desc(a_lo + ks * 2 * kLboA, kLboA, kSboA);
-                    const uint64_t dbh = umma_smem_desc(b_hi + ks * 2 * kLboB, kLboB, kSboB);
-                    const uint64_t dbl = umma_smem_desc(b_lo + ks * 2 * kLboB, kLboB, kSboB);
-                    umma_tf32(tmem, dah, dbh, (mma_commits > 0 || ks > 0) ? 1u : 0u);
-                    umma_tf32(tmem, dal, dbh, 1u);
-                    umma_tf32(tmem, dah, dbl, 1u);
+                fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
+                tc_fence_before();
+                mbar_arrive(&sm.bar_full);
+                // ring slot `slot` may be refilled once EVERY compute thread has consumed it, i.e. once this
+                // batch's tiles_full phase has completed
+                if (k + 2 < nchunks) {
+                    mbar_wait(&sm.bar_full, gc & 1);
+                    load_records(k + 2, gc + 2);
                 }
-                umma_commit(&sm.bar_mma);
             }
-            mma_commits++;
-            if (warp == 0 && k + 2 < nchunks) issue(k + 2);   // ring slot k&1 is free again
         }
-    }
+        if (!is_compute) gc += (lane == 0) ? 0 : nchunks;   // lanes 1..31 of the control warp just keep count
+        __syncthreads();
+    } while (!last);
 
     // ---- epilogue: accumulator row -> logits ------------------------------------------------------
-    float acc[32];
-    if (mma_commits > 0) {
-        mbar_wait(&sm.bar_mma, (mma_commits - 1) & 1);
-        tc_fence_after();
-        tmem_load_32(tmem + (static_cast<uint32_t>(warp * 32) << 16), acc);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    }
-    if (live) {
-        float *dst = p.out.logits + n * C;
-        if (PROB) {
-            const float zsum = acc[C];
-            if (zsum > 1e-9f) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) acc[c] = __fdiv_rn(acc[c], zsum);
-            } else {
-#pragma unroll
-                for (int c = 0; c < C; ++c) acc[c] = (c < C - 1) ? static_cast<float>(1.0 / (C - 1)) : 0.f;
-            }
-            p.out.bin_logits[n] = 1.f - keep;
-            p.out.density[n] = dens;
-            p.out.probability[n] = zsum;
-        }
-        if ((C & 1) == 0) {
-#pragma unroll
-            for (int c = 0; c < C; c += 2) __stcs(reinterpret_cast<float2 *>(dst + c), make_float2(acc[c], acc[c + 1]));
+    if (is_compute) {
+        float acc[32];
+        if (gc > 0) {
+            mbar_wait(&sm.bar_free, (gc - 1) & 1);
+            tc_fence_after();
+            tmem_load_32(tmem + (static_cast<uint32_t>(warp * 32) << 16), acc);
         } else {
 #pragma unroll
-            for (int c = 0; c < C; ++c) dst[c] = acc[c];
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
         }
-    } else if (valid) {
-        render_one_point<C, PROB>(p, n, px, py, pz);   // point n does not sit in voxel n
+        if (live) {
+            float *dst = p.out.logits + n * C;
+            if (PROB) {
+                const float zsum = acc[C];
+                if (zsum > 1e-9f) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[c] = __fdiv_rn(acc[c], zsum);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[c] = (c < C - 1) ? static_cast<float>(1.0 / (C - 1)) : 0.f;
+                }
+                p.out.bin_logits[n] = 1.f - keep;
+                p.out.density[n] = dens;
+                p.out.probability[n] = zsum;
+            }
+            if ((C & 1) == 0) {
+#pragma unroll
+                for (int c = 0; c < C; c += 2) __stcs(reinterpret_cast<float2 *>(dst + c), make_float2(acc[c], acc[c + 1]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) dst[c] = acc[c];
+            }
+        } else if (valid) {
+            render_one_point<C, PROB>(p, n, px, py, pz);   // point n does not sit in voxel n
+        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (!is_compute) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
     }
 }
@@ -395,7 +438,7 @@ static int launch_render_tc_t(const RenderParams &rp_in, cudaStream_t stream) {
     const long long grid = static_cast<long long>(nbx) * rp.nby * rp.nzc;
     const size_t smem = sizeof(TcSmem<C>);
     if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_before, stream));
-    render_tc_kernel<C, PROB><<<static_cast<unsigned>(grid), kTcThreads, smem, stream>>>(rp);
+    render_tc_kernel<C, PROB><<<static_cast<unsigned>(grid), kTcThreads + 32, smem, stream>>>(rp);
     GF_CUDA_TRY(cudaGetLastError());
     if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_after, stream));
     return GF_OK;

@@ -98,7 +98,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n"   // suspend-time hint (ns): sleep, don't poll
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)

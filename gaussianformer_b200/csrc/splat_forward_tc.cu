@@ -57,7 +57,7 @@ struct TcSmem {
     alignas(8) uint64_t bar_full;
     alignas(8) uint64_t bar_free;
     uint32_t tmem_base;
-    int warp_count[kTcThreads / 32];
+    int warp_count[2][kTcThreads / 32];   // double-buffered: one barrier per compaction round
     int nlist, last;
 };
 
@@ -208,16 +208,28 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
         if (is_compute) {
             int nlist = 0;
             while (cpos < ncand && nlist + kTcThreads <= kTcSeg) {
-                const int i = cpos + tid;
-                uint2 entry = make_uint2(0u, 0u);
-                bool hit = false;
-                if (i < ncand) {
-                    const int g = __ldg(cand + i);
-                    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p.boxes) + g);
+                // fetch up to kPre rounds of candidates and their boxes before touching any of them
+                // (two dependent L2/HBM round trips per super-round instead of per round)
+                constexpr int kPre = 4;
+                int gg[kPre];
+                uint4 bb[kPre];
+#pragma unroll
+                for (int u = 0; u < kPre; ++u) {
+                    const int i = cpos + u * kTcThreads + tid;
+                    gg[u] = i < ncand ? __ldg(cand + i) : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < kPre; ++u)
+                    bb[u] = gg[u] >= 0 ? __ldg(reinterpret_cast<const uint4 *>(p.boxes) + gg[u]) : make_uint4(1u, 1u, 1u, 1u);
+#pragma unroll
+                for (int u = 0; u < kPre; ++u) {
+                    if (cpos >= ncand || nlist + kTcThreads > kTcSeg) break;   // uniform
+                    const uint4 b = bb[u];
                     const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16,
                                    z0 = b.z & 0xffffu, z1 = b.z >> 16;
-                    hit = x0 <= bX1 && x1 >= static_cast<uint32_t>(binX0) && y0 <= bY1 && y1 >= static_cast<uint32_t>(binY0) &&
-                          z0 <= bZ1 && z1 >= static_cast<uint32_t>(binZ0) && b.w == 0u;
+                    const bool hit = gg[u] >= 0 && x0 <= bX1 && x1 >= static_cast<uint32_t>(binX0) && y0 <= bY1 &&
+                                     y1 >= static_cast<uint32_t>(binY0) && z0 <= bZ1 && z1 >= static_cast<uint32_t>(binZ0) &&
+                                     b.w == 0u;
                     // box relative to the bin as three bit masks
                     const int rx0 = max(static_cast<int>(x0) - binX0, 0), rx1 = min(static_cast<int>(x1) - binX0, kTcBinX - 1);
                     const int ry0 = max(static_cast<int>(y0) - binY0, 0), ry1 = min(static_cast<int>(y1) - binY0, kTcBinY - 1);
@@ -225,21 +237,21 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
                     const uint32_t xm = ((2u << rx1) - 1u) & ~((1u << rx0) - 1u);
                     const uint32_t ym = ((2u << ry1) - 1u) & ~((1u << ry0) - 1u);
                     const uint32_t zm = ((2u << rz1) - 1u) & ~((1u << rz0) - 1u);
-                    entry = make_uint2(xm | (ym << 4) | (zm << 8), static_cast<uint32_t>(g));
-                }
-                const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
-                if (lane == 0) sm.warp_count[warp] = __popc(ballot);
-                compute_warps_sync();
-                int off = nlist, total = 0;
+                    const uint2 entry = make_uint2(xm | (ym << 4) | (zm << 8), static_cast<uint32_t>(gg[u]));
+                    const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+                    if (lane == 0) sm.warp_count[u & 1][warp] = __popc(ballot);
+                    compute_warps_sync();
+                    int off = nlist, total = 0;
 #pragma unroll
-                for (int k = 0; k < kTcThreads / 32; ++k) {
-                    const int c = sm.warp_count[k];
-                    if (k < warp) off += c;
-                    total += c;
+                    for (int k = 0; k < kTcThreads / 32; ++k) {
+                        const int c = sm.warp_count[u & 1][k];
+                        if (k < warp) off += c;
+                        total += c;
+                    }
+                    if (hit) sm.list[off + __popc(ballot & lanemask_lt())] = entry;
+                    nlist += total;
+                    cpos += kTcThreads;
                 }
-                if (hit) sm.list[off + __popc(ballot & lanemask_lt())] = entry;
-                nlist += total;
-                cpos += kTcThreads;
                 compute_warps_sync();
             }
             // pad the last batch with empty entries (mask 0 never matches)
@@ -323,19 +335,18 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
                         keep *= (1.f - E);
                     }
                 }
-                // ---- my 4 classes of Gaussian kk for the S tile ---------------------------------------------
-                const int kk = tid & (kTcK - 1), ng = tid >> 4;   // 8 groups of 4 classes
-                float sv[4] = {0.f, 0.f, 0.f, 0.f};
-                if (ng * 4 < C + (PROB ? 1 : 0) && kk < cnt) {
-                    if (ng < CP / 4) {
-                        const float4 s4 = reinterpret_cast<const float4 *>(&sm.rec[slot][kk * REC])[3 + ng];
-                        sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
-                    }
+                // ---- my classes of Gaussian kk for the S tile: lane -> (class mod 8, kk mod 4) makes both the
+                //      scalar stores below bank-conflict free --------------------------------------------------
+                const int kk = (lane & 3) + 4 * warp, nn_low = lane >> 2;
+                constexpr int kNg = (C + (PROB ? 1 : 0) + 7) / 8;   // groups of 8 classes actually used
+                float sv[kNg];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (ng * 4 + i >= C) sv[i] = 0.f;
-                        if (PROB && ng * 4 + i == C) sv[i] = 1.f;   // all-ones column -> Z
-                    }
+                for (int e8 = 0; e8 < kNg; ++e8) {
+                    const int nn = nn_low + 8 * e8;
+                    float v = 0.f;
+                    if (kk < cnt && nn < C) v = sm.rec[slot][kk * REC + kGeomFloats + nn];
+                    if (PROB && kk < cnt && nn == C) v = 1.f;       // all-ones column -> Z
+                    sv[e8] = v;
                 }
 
                 // ---- the operand tiles are free once the previous batch's MMAs have completed -----------
@@ -355,16 +366,14 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
                     *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.a_lo) + a_row + kc * kLboA) =
                         make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
-                if (ng * 4 < C + (PROB ? 1 : 0)) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int nn = ng * 4 + i;
-                        const uint32_t off = (nn & 7) * 16 + (nn >> 3) * kSboB + (kk >> 2) * kLboB + (kk & 3) * 4;
-                        const uint32_t hi = __float_as_uint(sv[i]) & 0xFFFFE000u;
-                        const uint32_t lo = __float_as_uint(sv[i] - __uint_as_float(hi));
-                        *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sm.b_hi) + off) = hi;
-                        *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sm.b_lo) + off) = lo;
-                    }
+                for (int e8 = 0; e8 < kNg; ++e8) {
+                    const int nn = nn_low + 8 * e8;
+                    const uint32_t off = (nn & 7) * 16 + (nn >> 3) * kSboB + (kk >> 2) * kLboB + (kk & 3) * 4;
+                    const uint32_t hi = __float_as_uint(sv[e8]) & 0xFFFFE000u;
+                    const uint32_t lo = __float_as_uint(sv[e8] - __uint_as_float(hi));
+                    *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sm.b_hi) + off) = hi;
+                    *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sm.b_lo) + off) = lo;
                 }
                 fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
                 tc_fence_before();

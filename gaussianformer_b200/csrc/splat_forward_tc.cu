@@ -126,7 +126,7 @@ __device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1,
 // the control warp: it owns tensor memory and its lane 0 issues the MMAs, so no compute warp ever
 // serialises the others behind descriptor arithmetic.  All hand-offs inside the batch loop are
 // mbarriers (no CTA-wide barrier):
-//   rec_full[2]   records of a batch have landed (cp.async arrivals of the 128 compute threads)
+//   rec_full[2]   records of a batch have landed (cp.async arrivals of the control warp's 32 lanes)
 //   tiles_full    all compute threads have written their part of the A / B tiles
 //   tiles_free    the MMAs that read those tiles have completed (tcgen05.commit)
 template <int C, bool PROB>
@@ -143,9 +143,7 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
     const int H = p.d.H, W = p.d.W, D = p.d.D;
 
     // ---- my voxel (compute threads) ---------------------------------------------------------------------
-    const int bin = blockIdx.x / p.nzc, zc = blockIdx.x % p.nzc;
-    const int bxi = bin / p.nby, byi = bin % p.nby;
-    const int binX0 = bxi * kTcBinX, binY0 = byi * kTcBinY, binZ0 = zc * kTcBinZ;
+    const int binX0 = blockIdx.z * kTcBinX, binY0 = blockIdx.y * kTcBinY, binZ0 = blockIdx.x * kTcBinZ;
     const int lx = lane >> 3, ly = (lane >> 1) & 3, lz = 2 * (warp & 3) + (lane & 1);   // warp = 4 x 4 x 2 voxels
     const int X = binX0 + lx, Y = binY0 + ly, Z = binZ0 + lz;
     const bool valid = is_compute && X < H && Y < W && Z < D;
@@ -158,9 +156,20 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
         if (p.points_int) {
             ix = p.points_int[3 * n]; iy = p.points_int[3 * n + 1]; iz = p.points_int[3 * n + 2];
         } else {
-            ix = voxel_coord(px, p.d.pc_min[0], p.d.grid_size);
-            iy = voxel_coord(py, p.d.pc_min[1], p.d.grid_size);
-            iz = voxel_coord(pz, p.d.pc_min[2], p.d.grid_size);
+            // exact trunc((p - origin) / cell) costs three IEEE divisions; a point that lies well inside
+            // voxel (X,Y,Z) by a cheap reciprocal estimate needs none (the estimate is off by < 1e-5 cells)
+            const float inv = __frcp_rn(p.d.grid_size);
+            const float fx = (px - p.d.pc_min[0]) * inv - static_cast<float>(X);
+            const float fy = (py - p.d.pc_min[1]) * inv - static_cast<float>(Y);
+            const float fz = (pz - p.d.pc_min[2]) * inv - static_cast<float>(Z);
+            const float lo_m = 1e-3f, hi_m = 1.f - 1e-3f;
+            if (fx > lo_m && fx < hi_m && fy > lo_m && fy < hi_m && fz > lo_m && fz < hi_m) {
+                ix = X; iy = Y; iz = Z;
+            } else {
+                ix = voxel_coord(px, p.d.pc_min[0], p.d.grid_size);
+                iy = voxel_coord(py, p.d.pc_min[1], p.d.grid_size);
+                iz = voxel_coord(pz, p.d.pc_min[2], p.d.grid_size);
+            }
         }
         canon = ix == X && iy == Y && iz == Z;
         if (!canon) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
@@ -172,8 +181,8 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
 
     // ---- one-time setup: barriers, tensor memory, zeroed S tiles ---------------------------------
     if (tid == 0) {
-        mbar_init(&sm.bar_rec[0], kTcThreads);
-        mbar_init(&sm.bar_rec[1], kTcThreads);
+        mbar_init(&sm.bar_rec[0], 32);
+        mbar_init(&sm.bar_rec[1], 32);
         mbar_init(&sm.bar_full, kTcThreads);
         mbar_init(&sm.bar_free, 1);
         mbar_fence_init();
@@ -183,7 +192,10 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
                      "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = tid; i < kTcN * kTcK; i += kTcThreads + 32) { sm.b_hi[i] = 0u; sm.b_lo[i] = 0u; }
+    for (int i = tid; i < kTcN * kTcK / 4; i += kTcThreads + 32) {
+        reinterpret_cast<uint4 *>(sm.b_hi)[i] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4 *>(sm.b_lo)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -196,7 +208,8 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
     const uint32_t a_row = (tid & 7) * 16 + ((tid & 127) >> 3) * kSboA;
 
     // ---- candidates: the ascending list of this bin's supertile ------------------------------------
-    const int s = (binX0 / p.st) * p.nsy + (binY0 / p.st);
+    const int st_shift = 31 - __clz(p.st);   // the supertile edge is a power of two
+    const int s = (binX0 >> st_shift) * p.nsy + (binY0 >> st_shift);
     const int ncand = p.counts[s];
     const int32_t *cand = p.lists + static_cast<size_t>(s) * p.d.G;
     const uint32_t bX1 = min(binX0 + kTcBinX, H) - 1, bY1 = min(binY0 + kTcBinY, W) - 1, bZ1 = min(binZ0 + kTcBinZ, D) - 1;
@@ -267,43 +280,49 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
         const int nchunks = (nlist + kTcK - 1) / kTcK;
 
         if (!is_compute) {
-            // ======================= control warp: tensor-core issue ====================================
-            if (lane == 0) {
-                const uint32_t a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
-                const uint32_t b_hi = smem_u32(sm.b_hi), b_lo = smem_u32(sm.b_lo);
-                uint64_t dah[kTcK / 8], dal[kTcK / 8], dbh[kTcK / 8], dbl[kTcK / 8];
-#pragma unroll
-                for (int ks = 0; ks < kTcK / 8; ++ks) {
-                    dah[ks] = umma_smem_desc(a_hi + ks * 2 * kLboA, kLboA, kSboA);
-                    dal[ks] = umma_smem_desc(a_lo + ks * 2 * kLboA, kLboA, kSboA);
-                    dbh[ks] = umma_smem_desc(b_hi + ks * 2 * kLboB, kLboB, kSboB);
-                    dbl[ks] = umma_smem_desc(b_lo + ks * 2 * kLboB, kLboB, kSboB);
-                }
-                for (int k = 0; k < nchunks; ++k, ++gc) {
-                    mbar_wait(&sm.bar_full, gc & 1);
-                    tc_fence_after();
-#pragma unroll
-                    for (int ks = 0; ks < kTcK / 8; ++ks) {
-                        umma_tf32(tmem, dah[ks], dbh[ks], (gc > 0 || ks > 0) ? 1u : 0u);
-                        umma_tf32(tmem, dal[ks], dbh[ks], 1u);
-                        umma_tf32(tmem, dah[ks], dbl[ks], 1u);
-                    }
-                    umma_commit(&sm.bar_free);
-                }
-            }
-        } else {
-            // ======================= compute warps: W / S tiles ===========================================
+            // ======================= control warp: record ring + tensor-core issue ========================
             auto load_records = [&](int k, uint32_t g_index) {   // batch k of this segment -> ring slot g_index & 1
                 const int slot = g_index & 1;
-                const int row = tid >> 3;                          // 16 records x 8 chunks of 16 bytes
-                if (k * kTcK + row < nlist) {
-                    const uint32_t g = sm.list[k * kTcK + row].y;
-                    cp_async_16(&sm.rec[slot][row * REC + (tid & 7) * 4], p.records + static_cast<size_t>(g) * REC + (tid & 7) * 4);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {                      // 16 records x 8 chunks of 16 bytes = 128 copies
+                    const int piece = lane + 32 * q, row = piece >> 3, col = (piece & 7) * 4;
+                    if (k * kTcK + row < nlist) {
+                        const uint32_t g = sm.list[k * kTcK + row].y;
+                        cp_async_16(&sm.rec[slot][row * REC + col], p.records + static_cast<size_t>(g) * REC + col);
+                    }
                 }
                 cp_async_arrive(&sm.bar_rec[slot]);
             };
+            const uint32_t a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
+            const uint32_t b_hi = smem_u32(sm.b_hi), b_lo = smem_u32(sm.b_lo);
             if (nchunks > 0) load_records(0, gc);
             if (nchunks > 1) load_records(1, gc + 1);
+            for (int k = 0; k < nchunks; ++k, ++gc) {
+                // all compute threads have written the tiles of this batch (and are done with its records)
+                uint32_t spins = 0;
+                while (!mbar_try_wait(&sm.bar_full, gc & 1)) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 22)) __trap();
+                }
+                if (lane == 0) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < kTcK / 8; ++ks) {
+                        const uint64_t dah = umma_smem_desc(a_hi + ks * 2 * kLboA, kLboA, kSboA);
+                        const uint64_t dal = umma_smem_desc(a_lo + ks * 2 * kLboA, kLboA, kSboA);
+                        const uint64_t dbh = umma_smem_desc(b_hi + ks * 2 * kLboB, kLboB, kSboB);
+                        const uint64_t dbl = umma_smem_desc(b_lo + ks * 2 * kLboB, kLboB, kSboB);
+                        umma_tf32(tmem, dah, dbh, (gc > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(tmem, dal, dbh, 1u);
+                        umma_tf32(tmem, dah, dbl, 1u);
+                    }
+                    umma_commit(&sm.bar_free);
+                }
+                __syncwarp();
+                if (k + 2 < nchunks) load_records(k + 2, gc + 2);   // ring slot gc & 1 is free again
+            }
+        } else {
+            // ======================= compute warps: W / S tiles ===========================================
             for (int k = 0; k < nchunks; ++k, ++gc) {
                 const int slot = gc & 1;
                 const int cnt = min(kTcK, nlist - k * kTcK);
@@ -378,15 +397,8 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
                 fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
                 tc_fence_before();
                 mbar_arrive(&sm.bar_full);
-                // ring slot `slot` may be refilled once EVERY compute thread has consumed it, i.e. once this
-                // batch's tiles_full phase has completed
-                if (k + 2 < nchunks) {
-                    mbar_wait(&sm.bar_full, gc & 1);
-                    load_records(k + 2, gc + 2);
-                }
             }
         }
-        if (!is_compute) gc += (lane == 0) ? 0 : nchunks;   // lanes 1..31 of the control warp just keep count
         __syncthreads();
     } while (!last);
 
@@ -444,10 +456,11 @@ static int launch_render_tc_t(const RenderParams &rp_in, cudaStream_t stream) {
     rp.nby = (rp.d.W + kTcBinY - 1) / kTcBinY;
     rp.nzc = (rp.d.D + kTcBinZ - 1) / kTcBinZ;
     const int nbx = (rp.d.H + kTcBinX - 1) / kTcBinX;
-    const long long grid = static_cast<long long>(nbx) * rp.nby * rp.nzc;
+    GF_REQUIRE(rp.nby <= 65535 && nbx <= 65535, GF_ERR_UNSUPPORTED, "splat: grid too large for the render launch");
+    const dim3 grid(rp.nzc, rp.nby, nbx);
     const size_t smem = sizeof(TcSmem<C>);
     if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_before, stream));
-    render_tc_kernel<C, PROB><<<static_cast<unsigned>(grid), kTcThreads + 32, smem, stream>>>(rp);
+    render_tc_kernel<C, PROB><<<grid, kTcThreads + 32, smem, stream>>>(rp);
     GF_CUDA_TRY(cudaGetLastError());
     if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_after, stream));
     return GF_OK;

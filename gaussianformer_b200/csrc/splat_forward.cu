@@ -24,20 +24,36 @@ namespace gf {
 
 extern thread_local cudaEvent_t g_ev_before, g_ev_after;  // measurement hooks (cabi.cu)
 
+constexpr int kQuadSeg = 512;   // list entries resolved per segment
+
 template <int C>
 struct RenderSmem {
     static constexpr int REC = rec_floats(C);
     alignas(128) float stage[2][kChunk * REC];
-    alignas(16) uint4 list[kSeg];  // x,y,z packed bounds + Gaussian index
-    alignas(8) uint64_t bar[2];
-    int warp_count[kRenderThreads / 32];
-    int nlist;
+    alignas(8) uint2 list[kQuadSeg + kChunk];  // x: box relative to the bin as bit masks, y: index | warp-hit bits
+    int warp_count[2][kRenderThreads / 32];
 };
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// SIMT render kernel ("quad" kernel): bin = 8 x 4 columns x 16 z, one z-quad (4 voxels) per thread with
+// 4 x C accumulators in registers; a warp covers 4 x 4 x 8 voxels.
+//   * Phase A resolves the bin's ordered Gaussian list; each entry carries the box clipped to the bin
+//     as bit masks (x: 8 bits, y: 4 bits, z: 16 bits) and one "this warp's footprint is touched" bit
+//     per warp, so Phase B never unpacks coordinates.
+//   * Phase B streams the records (cp.async, double buffered); every warp walks only the records that
+//     touch its footprint (ballot -> bit loop), a lane tests its column with one AND and its four
+//     voxels with one shift, and the class accumulation runs on packed fp32 pairs (FFMA2).
 template <int C, bool PROB>
 __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kernel(const RenderParams p) {
     constexpr int REC = rec_floats(C);
-    constexpr int CP = REC - kGeomFloats;
+    constexpr int CP2 = (C + 1) / 2;   // packed class pairs
+    static_assert(REC == 32, "one record = 128 bytes");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RenderSmem<C> &sm = *reinterpret_cast<RenderSmem<C> *>(smem_raw);
 
@@ -45,14 +61,9 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
     const int H = p.d.H, W = p.d.W, D = p.d.D;
 
     // ---- which voxels are mine -------------------------------------------------------------------
-    const int bin = blockIdx.x / p.nzc, zc = blockIdx.x % p.nzc;
-    const int bxi = bin / p.nby, byi = bin % p.nby;
-    const int binX0 = bxi * kBinX, binY0 = byi * kBinY, binZ0 = zc * kBinZ;
-    const int wX0 = binX0 + (warp & 1) * 4;       // warp footprint: 4 x, 4 y, 8 z
-    const int wZ0 = binZ0 + (warp >> 1) * 8;
-    const int X = wX0 + (lane >> 3);
-    const int Y = binY0 + ((lane >> 1) & 3);
-    const int Z0 = wZ0 + (lane & 1) * 4;
+    const int binX0 = blockIdx.z * kBinX, binY0 = blockIdx.y * kBinY, binZ0 = blockIdx.x * kBinZ;
+    const int lx = (warp & 1) * 4 + (lane >> 3), ly = (lane >> 1) & 3, lq = (warp >> 1) * 2 + (lane & 1);  // quad 0..3
+    const int X = binX0 + lx, Y = binY0 + ly, Z0 = binZ0 + 4 * lq;
     const bool col_ok = X < H && Y < W;
     const long long n0 = (static_cast<long long>(X) * W + Y) * D + Z0;
     const bool vec_ok = (D & 3) == 0;  // then n0 % 4 == 0 and Z0+3 < D whenever Z0 < D
@@ -64,6 +75,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
         vox_ok[v] = col_ok && (Z0 + v) < D;
         px[v] = py[v] = pz[v] = 0.f;
     }
+    bool canon = true;
     if (col_ok && Z0 < D) {
         if (vec_ok) {
             const float4 *src = reinterpret_cast<const float4 *>(p.pts + 3 * n0);
@@ -80,8 +92,9 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                     pz[v] = __ldg(p.pts + 3 * (n0 + v) + 2);
                 }
         }
-        // canonical-order check: point n must lie in voxel n
-        bool canon = true;
+        // canonical-order check: point n must lie in voxel n.  A cheap reciprocal estimate settles every
+        // point that is not within 1e-3 cells of a voxel face; only those pay the exact IEEE divisions.
+        const float inv = __frcp_rn(p.d.grid_size);
 #pragma unroll
         for (int v = 0; v < kVox; ++v)
             if (vox_ok[v]) {
@@ -91,100 +104,126 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                     iy = p.points_int[3 * (n0 + v) + 1];
                     iz = p.points_int[3 * (n0 + v) + 2];
                 } else {
-                    ix = voxel_coord(px[v], p.d.pc_min[0], p.d.grid_size);
-                    iy = voxel_coord(py[v], p.d.pc_min[1], p.d.grid_size);
-                    iz = voxel_coord(pz[v], p.d.pc_min[2], p.d.grid_size);
+                    const float fx = (px[v] - p.d.pc_min[0]) * inv - static_cast<float>(X);
+                    const float fy = (py[v] - p.d.pc_min[1]) * inv - static_cast<float>(Y);
+                    const float fz = (pz[v] - p.d.pc_min[2]) * inv - static_cast<float>(Z0 + v);
+                    const float lo_m = 1e-3f, hi_m = 1.f - 1e-3f;
+                    if (fx > lo_m && fx < hi_m && fy > lo_m && fy < hi_m && fz > lo_m && fz < hi_m) {
+                        ix = X; iy = Y; iz = Z0 + v;
+                    } else {
+                        ix = voxel_coord(px[v], p.d.pc_min[0], p.d.grid_size);
+                        iy = voxel_coord(py[v], p.d.pc_min[1], p.d.grid_size);
+                        iz = voxel_coord(pz[v], p.d.pc_min[2], p.d.grid_size);
+                    }
                 }
                 canon = canon && ix == X && iy == Y && iz == Z0 + v;
             }
         if (!canon) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
     }
+    // entry word: x mask [0,8) | y mask [8,12) | z mask [16,32)
+    const uint32_t my_xy = (1u << lx) | (1u << (8 + ly));
+    const int my_zshift = 16 + 4 * lq;
 
-    float acc[kVox][C];
+    float2 acc[kVox][CP2];
     float zsum[kVox], dens[kVox], keep[kVox];
 #pragma unroll
     for (int v = 0; v < kVox; ++v) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[v][c] = 0.f;
+        for (int c = 0; c < CP2; ++c) acc[v][c] = make_float2(0.f, 0.f);
         zsum[v] = 0.f; dens[v] = 0.f; keep[v] = 1.f;
     }
 
-    if (tid == 0) {
-        mbar_init(&sm.bar[0], 1);
-        mbar_init(&sm.bar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    uint32_t use[2] = {0, 0};  // how many times each stage's barrier has completed (parity source)
-
     // ---- candidates: the ascending list of this bin's supertile ------------------------------------
-    const int s = (binX0 / p.st) * p.nsy + (binY0 / p.st);
+    const int st_shift = 31 - __clz(p.st);
+    const int s = (binX0 >> st_shift) * p.nsy + (binY0 >> st_shift);
     const int ncand = p.counts[s];
     const int32_t *cand = p.lists + static_cast<size_t>(s) * p.d.G;
     const uint32_t bX1 = min(binX0 + kBinX, H) - 1, bY1 = min(binY0 + kBinY, W) - 1, bZ1 = min(binZ0 + kBinZ, D) - 1;
 
     int cpos = 0;
     while (cpos < ncand) {
-        // ======================= Phase A: fill sm.list with up to kSeg survivors =====================
-        if (tid == 0) sm.nlist = 0;
-        __syncthreads();
+        // ======================= Phase A: ordered survivors of the box test ==========================
         int nlist = 0;
-        while (cpos < ncand && nlist + kRenderThreads <= kSeg) {
-            const int i = cpos + tid;
-            uint4 entry = make_uint4(1u, 1u, 1u, 0u);
-            bool hit = false;
-            if (i < ncand) {
-                const int g = __ldg(cand + i);
-                const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p.boxes) + g);
-                hit = (b.x & 0xffffu) <= bX1 && (b.x >> 16) >= static_cast<uint32_t>(binX0) &&
-                      (b.y & 0xffffu) <= bY1 && (b.y >> 16) >= static_cast<uint32_t>(binY0) &&
-                      (b.z & 0xffffu) <= bZ1 && (b.z >> 16) >= static_cast<uint32_t>(binZ0) && b.w == 0u;
-                entry = make_uint4(b.x, b.y, b.z, static_cast<uint32_t>(g));
+        while (cpos < ncand && nlist + kRenderThreads <= kQuadSeg) {
+            constexpr int kPre = 4;   // rounds fetched together (memory-level parallelism)
+            int gg[kPre];
+            uint4 bb[kPre];
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) {
+                const int i = cpos + u * kRenderThreads + tid;
+                gg[u] = i < ncand ? __ldg(cand + i) : -1;
             }
-            const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) sm.warp_count[warp] = __popc(ballot);
-            __syncthreads();
-            int off = nlist;
 #pragma unroll
-            for (int k = 0; k < kRenderThreads / 32; ++k)
-                if (k < warp) off += sm.warp_count[k];
-            int total = 0;
+            for (int u = 0; u < kPre; ++u)
+                bb[u] = gg[u] >= 0 ? __ldg(reinterpret_cast<const uint4 *>(p.boxes) + gg[u]) : make_uint4(1u, 1u, 1u, 1u);
 #pragma unroll
-            for (int k = 0; k < kRenderThreads / 32; ++k) total += sm.warp_count[k];
-            if (hit) sm.list[off + __popc(ballot & lanemask_lt())] = entry;
-            nlist += total;
-            cpos += kRenderThreads;
+            for (int u = 0; u < kPre; ++u) {
+                if (cpos >= ncand || nlist + kRenderThreads > kQuadSeg) break;   // uniform
+                const uint4 b = bb[u];
+                const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16,
+                               z0 = b.z & 0xffffu, z1 = b.z >> 16;
+                const bool hit = gg[u] >= 0 && x0 <= bX1 && x1 >= static_cast<uint32_t>(binX0) && y0 <= bY1 &&
+                                 y1 >= static_cast<uint32_t>(binY0) && z0 <= bZ1 && z1 >= static_cast<uint32_t>(binZ0) &&
+                                 b.w == 0u;
+                const int rx0 = max(static_cast<int>(x0) - binX0, 0), rx1 = min(static_cast<int>(x1) - binX0, kBinX - 1);
+                const int ry0 = max(static_cast<int>(y0) - binY0, 0), ry1 = min(static_cast<int>(y1) - binY0, kBinY - 1);
+                const int rz0 = max(static_cast<int>(z0) - binZ0, 0), rz1 = min(static_cast<int>(z1) - binZ0, kBinZ - 1);
+                const uint32_t xm = ((2u << rx1) - 1u) & ~((1u << rx0) - 1u);
+                const uint32_t ym = ((2u << ry1) - 1u) & ~((1u << ry0) - 1u);
+                const uint32_t zm = ((2u << rz1) - 1u) & ~((1u << rz0) - 1u);
+                // which warp footprints (x half, z half) does the clipped box touch?
+                uint32_t wh = 0;
+#pragma unroll
+                for (int wq = 0; wq < 4; ++wq)
+                    if ((xm & (0xFu << (4 * (wq & 1)))) && (zm & (0xFFu << (8 * (wq >> 1))))) wh |= 1u << wq;
+                const uint2 entry = make_uint2(xm | (ym << 8) | (zm << 16), static_cast<uint32_t>(gg[u]) | (wh << 28));
+                const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) sm.warp_count[u & 1][warp] = __popc(ballot);
+                __syncthreads();
+                int off = nlist, total = 0;
+#pragma unroll
+                for (int k = 0; k < kRenderThreads / 32; ++k) {
+                    const int c = sm.warp_count[u & 1][k];
+                    if (k < warp) off += c;
+                    total += c;
+                }
+                if (hit) sm.list[off + __popc(ballot & lanemask_lt())] = entry;
+                nlist += total;
+                cpos += kRenderThreads;
+            }
             __syncthreads();
         }
+        // pad the last batch with empty entries (no warp-hit bits, so nobody visits them)
+        if (tid < kChunk && nlist + tid < ((nlist + kChunk - 1) / kChunk) * kChunk) sm.list[nlist + tid] = make_uint2(0u, 0u);
+        __syncthreads();
 
         // ======================= Phase B: stream records and accumulate ==============================
         const int nchunks = (nlist + kChunk - 1) / kChunk;
-        auto issue = [&](int k) {  // warp 0 stages chunk k into ring slot k&1
+        auto issue = [&](int k) {  // all threads stage batch k into ring slot k&1: 32 records x 8 x 16 B = 256 copies
             const int slot = k & 1;
-            const int cnt = min(kChunk, nlist - k * kChunk);
-            if (lane == 0) mbar_expect_tx(&sm.bar[slot], cnt * REC * 4);
-            __syncwarp();
-            if (lane < cnt) {
-                const uint32_t g = sm.list[k * kChunk + lane].w;
-                tma_load_1d(&sm.stage[slot][lane * REC], p.records + static_cast<size_t>(g) * REC, REC * 4,
-                            &sm.bar[slot]);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int piece = tid + kRenderThreads * q, row = piece >> 3, col = (piece & 7) * 4;
+                if (k * kChunk + row < nlist) {
+                    const uint32_t g = sm.list[k * kChunk + row].y & 0x0FFFFFFFu;
+                    cp_async16(&sm.stage[slot][row * REC + col], p.records + static_cast<size_t>(g) * REC + col);
+                }
             }
+            cp_async_commit();
         };
-        if (warp == 0 && nchunks > 0) issue(0);
+        if (nchunks > 0) issue(0);
         for (int k = 0; k < nchunks; ++k) {
             const int slot = k & 1;
-            if (warp == 0 && k + 1 < nchunks) issue(k + 1);
-            mbar_wait(&sm.bar[slot], use[slot] & 1);
-            use[slot]++;
-            const int cnt = min(kChunk, nlist - k * kChunk);
-            for (int j = 0; j < cnt; ++j) {
-                const uint4 b = sm.list[k * kChunk + j];
-                const int x0 = b.x & 0xffff, x1 = b.x >> 16, z0 = b.z & 0xffff, z1 = b.z >> 16;
-                // warp-uniform cull against this warp's 4x4x8 footprint
-                if (x1 < wX0 || x0 > wX0 + 3 || z1 < wZ0 || z0 > wZ0 + 7) continue;
-                const int y0 = b.y & 0xffff, y1 = b.y >> 16;
-                const bool act = X >= x0 && X <= x1 && Y >= y0 && Y <= y1 && z1 >= Z0 && z0 <= Z0 + 3;
-                if (act) {
+            if (k + 1 < nchunks) { issue(k + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+            __syncthreads();   // batch k has landed for everybody
+            // records that touch my warp's footprint, in ascending order
+            uint32_t todo = __ballot_sync(0xffffffffu, (sm.list[k * kChunk + lane].y >> (28 + warp)) & 1u);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t e = sm.list[k * kChunk + j].x;
+                const uint32_t zb = (e >> my_zshift) & 0xFu;
+                if ((e & my_xy) == my_xy && zb) {
                     const float4 *r4 = reinterpret_cast<const float4 *>(&sm.stage[slot][j * REC]);
                     const float4 g0 = r4[0], g1 = r4[1];
                     const float2 g2 = *reinterpret_cast<const float2 *>(r4 + 2);
@@ -200,8 +239,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                         float q = t1 * dx;
                         q = fmaf(t2, dy, q);
                         q = fmaf(g1.z * dz, dz, q);
-                        const bool in = (Z0 + v) >= z0 && (Z0 + v) <= z1;
-                        const float E = in ? ex2_approx(q) : 0.f;
+                        const float E = ((zb >> v) & 1u) ? ex2_approx(q) : 0.f;
                         wv[v] = g0.w * E;
                         if (PROB) {
                             zsum[v] += wv[v];
@@ -210,16 +248,13 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                         }
                     }
 #pragma unroll
-                    for (int c4 = 0; c4 < CP / 4; ++c4) {
+                    for (int c4 = 0; c4 < (C + 3) / 4; ++c4) {
                         const float4 s4 = r4[3 + c4];
-                        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int c = c4 * 4 + i;
-                            if (c < C) {
-#pragma unroll
-                                for (int v = 0; v < kVox; ++v) acc[v][c] = fmaf(sv[i], wv[v], acc[v][c]);
-                            }
+                        for (int v = 0; v < kVox; ++v) {
+                            const float2 ww = make_float2(wv[v], wv[v]);
+                            acc[v][2 * c4] = __ffma2_rn(make_float2(s4.x, s4.y), ww, acc[v][2 * c4]);
+                            if (2 * c4 + 1 < CP2) acc[v][2 * c4 + 1] = __ffma2_rn(make_float2(s4.z, s4.w), ww, acc[v][2 * c4 + 1]);
                         }
                     }
                 }
@@ -230,17 +265,20 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
 
     // ---- epilogue ----------------------------------------------------------------------------------
     if (!(col_ok && Z0 < D)) return;
+    float out[kVox][C];
+#pragma unroll
+    for (int v = 0; v < kVox; ++v)
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[v][c] = (c & 1) ? acc[v][c >> 1].y : acc[v][c >> 1].x;
     if (PROB) {
 #pragma unroll
         for (int v = 0; v < kVox; ++v) {
             if (zsum[v] > 1e-9f) {
-                const float inv = 1.f / zsum[v];
 #pragma unroll
-                for (int c = 0; c < C; ++c) acc[v][c] = __fdiv_rn(acc[v][c], zsum[v]);
-                (void)inv;
+                for (int c = 0; c < C; ++c) out[v][c] = __fdiv_rn(out[v][c], zsum[v]);
             } else {
 #pragma unroll
-                for (int c = 0; c < C; ++c) acc[v][c] = (c < C - 1) ? static_cast<float>(1.0 / (C - 1)) : 0.f;
+                for (int c = 0; c < C; ++c) out[v][c] = (c < C - 1) ? static_cast<float>(1.0 / (C - 1)) : 0.f;
             }
         }
     }
@@ -250,7 +288,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
 #pragma unroll
         for (int v = 0; v < kVox; ++v)
 #pragma unroll
-            for (int c = 0; c < C; ++c) flat[v * C + c] = acc[v][c];
+            for (int c = 0; c < C; ++c) flat[v * C + c] = out[v][c];
 #pragma unroll
         for (int i = 0; i < kVox * C / 4; ++i)
             __stcs(reinterpret_cast<float4 *>(dst) + i,
@@ -267,7 +305,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
         for (int v = 0; v < kVox; ++v)
             if (vox_ok[v]) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) dst[v * C + c] = acc[v][c];
+                for (int c = 0; c < C; ++c) dst[v * C + c] = out[v][c];
                 if (PROB) {
                     p.out.bin_logits[n0 + v] = 1.f - keep[v];
                     p.out.density[n0 + v] = dens[v];
@@ -309,7 +347,8 @@ static int launch_render_t(const RenderParams &rp, bool tile_path, int num_sms, 
     if (tile_path) {
         const size_t smem = sizeof(RenderSmem<C>);
         const int nbx = (rp.d.H + kBinX - 1) / kBinX;
-        const int grid = nbx * rp.nby * rp.nzc;
+        GF_REQUIRE(rp.nby <= 65535 && nbx <= 65535, GF_ERR_UNSUPPORTED, "splat: grid too large for the render launch");
+        const dim3 grid(rp.nzc, rp.nby, nbx);
         if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_before, stream));
         render_tile_kernel<C, PROB><<<grid, kRenderThreads, smem, stream>>>(rp);
         GF_CUDA_TRY(cudaGetLastError());

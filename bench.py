@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step is one forward pass of the splat op (pack + supertile binning + render; 4 kernel launches)
+A step is one forward pass of the splat op (pack + supertile lists + render; 3 kernel launches)
 over one synthetic sample of BASELINE.json configs[1]: `nuscenes_gs25600_solid.py` shape —
 25 600 Gaussians (+ the "empty" Gaussian) into the 200x200x16 grid, 18 classes, batch 1 per GPU.
 Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md "Measurement".
@@ -230,7 +230,7 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "render_tile_kernel<18,false>", "kernel_ms": render_ms,
+                "traffic": traffic, "kernel": "render_tc_kernel<18,false>" if os.environ.get("GF_B200_RENDER", "")[:1] == "t" else "render_tile_kernel<18,false>", "kernel_ms": render_ms,
                 "algorithmic_bytes": alg, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)"}
 
     # ---- e2e: public module, host (pinned) inputs, H2D + forward + argmax + D2H -------------------
@@ -287,7 +287,7 @@ def main():
                            "l2": f"{N_SETS} rotating input/output/workspace sets "
                                  f"({N_SETS * (alg + ws_bytes) / 1e6:.0f} MB) > 126 MB L2",
                            "parallelism": f"dp{world} (one sample per GPU, scalar loss all-reduce)"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * K, "roofline": roofline,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline,
                 "cpu_baseline": cpu_baseline}
         line.update(extras)
         print(json.dumps(line), flush=True)

@@ -1,21 +1,11 @@
 // Splat stage 2 — the render kernels (replaces FORWARD::renderCUDA, model/head/localagg/src/forward.cu:35-82
 // and the prob variant model/head/localagg_prob/src/forward.cu:35-102).
 //
-// render_tile_kernel (fast path, points in canonical voxel order):
-//   one 128-thread CTA per bin of 8x4 columns x 16 z.  Each thread owns a z-quad (4 consecutive
-//   voxels = 288 contiguous output bytes) and keeps 4 x C accumulators in registers.
-//   Phase A: the CTA resolves its own Gaussian list from the supertile list (ordered ballot
-//            compaction of packed boxes into shared memory; ascending index == reference order).
-//   Phase B: records of the listed Gaussians are staged 32 at a time into a double-buffered shared
-//            ring by per-record 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); every
-//            lane then reads the record by shared-memory broadcast, applies the exact integer-box
-//            test per voxel, evaluates exp2 of the pre-scaled quadratic form and accumulates.
-//   The kernel also verifies that its points really are in canonical order; if any thread finds
-//   a mismatch it raises GF_FLAG_GENERIC_PATH and the generic kernel (launched right after, a
-//   no-op otherwise) recomputes every output.
-//
-// render_points_kernel (generic path): one thread per point, arbitrary points (several per voxel,
-//   N != H*W*D), walks the supertile list with the exact box test.
+// render_tile_kernel    the default tile kernel for points in canonical voxel order (see its header
+//                       comment below); stray points are detected per voxel and re-evaluated exactly.
+// render_points_kernel  arbitrary points (N != H*W*D, several per voxel): one thread per point walks
+//                       the supertile list with the exact box test.
+// The tcgen05 variant of the tile kernel lives in splat_forward_tc.cu.
 #include <cstdlib>
 
 #include "splat_render.cuh"
@@ -25,12 +15,13 @@ namespace gf {
 extern thread_local cudaEvent_t g_ev_before, g_ev_after;  // measurement hooks (cabi.cu)
 
 constexpr int kQuadSeg = 512;   // list entries resolved per segment
+constexpr int kBatch = 64;      // records staged per ring slot (two 32-record ballots per batch)
 
 template <int C>
 struct RenderSmem {
     static constexpr int REC = rec_floats(C);
-    alignas(128) float stage[2][kChunk * REC];
-    alignas(8) uint2 list[kQuadSeg + kChunk];  // x: box relative to the bin as bit masks, y: index | warp-hit bits
+    alignas(128) float stage[2][kBatch * REC];
+    alignas(8) uint2 list[kQuadSeg + kBatch];  // x: box relative to the bin as bit masks, y: index | warp-hit bits
     int warp_count[2][kRenderThreads / 32];
 };
 
@@ -75,7 +66,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
         vox_ok[v] = col_ok && (Z0 + v) < D;
         px[v] = py[v] = pz[v] = 0.f;
     }
-    bool canon = true;
+    uint32_t stray = 0;   // bit v: point n0+v does not sit in voxel n0+v
     if (col_ok && Z0 < D) {
         if (vec_ok) {
             const float4 *src = reinterpret_cast<const float4 *>(p.pts + 3 * n0);
@@ -116,9 +107,9 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                         iz = voxel_coord(pz[v], p.d.pc_min[2], p.d.grid_size);
                     }
                 }
-                canon = canon && ix == X && iy == Y && iz == Z0 + v;
+                if (!(ix == X && iy == Y && iz == Z0 + v)) stray |= 1u << v;
             }
-        if (!canon) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
+        if (stray) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
     }
     // entry word: x mask [0,8) | y mask [8,12) | z mask [16,32)
     const uint32_t my_xy = (1u << lx) | (1u << (8 + ly));
@@ -194,18 +185,18 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
             __syncthreads();
         }
         // pad the last batch with empty entries (no warp-hit bits, so nobody visits them)
-        if (tid < kChunk && nlist + tid < ((nlist + kChunk - 1) / kChunk) * kChunk) sm.list[nlist + tid] = make_uint2(0u, 0u);
+        if (tid < kBatch && nlist + tid < ((nlist + kBatch - 1) / kBatch) * kBatch) sm.list[nlist + tid] = make_uint2(0u, 0u);
         __syncthreads();
 
         // ======================= Phase B: stream records and accumulate ==============================
-        const int nchunks = (nlist + kChunk - 1) / kChunk;
-        auto issue = [&](int k) {  // all threads stage batch k into ring slot k&1: 32 records x 8 x 16 B = 256 copies
+        const int nchunks = (nlist + kBatch - 1) / kBatch;
+        auto issue = [&](int k) {  // all threads stage batch k into ring slot k&1: 64 records x 8 x 16 B = 512 copies
             const int slot = k & 1;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < kBatch * 8 / kRenderThreads; ++q) {
                 const int piece = tid + kRenderThreads * q, row = piece >> 3, col = (piece & 7) * 4;
-                if (k * kChunk + row < nlist) {
-                    const uint32_t g = sm.list[k * kChunk + row].y & 0x0FFFFFFFu;
+                if (k * kBatch + row < nlist) {
+                    const uint32_t g = sm.list[k * kBatch + row].y & 0x0FFFFFFFu;
                     cp_async16(&sm.stage[slot][row * REC + col], p.records + static_cast<size_t>(g) * REC + col);
                 }
             }
@@ -217,11 +208,13 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
             if (k + 1 < nchunks) { issue(k + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
             __syncthreads();   // batch k has landed for everybody
             // records that touch my warp's footprint, in ascending order
-            uint32_t todo = __ballot_sync(0xffffffffu, (sm.list[k * kChunk + lane].y >> (28 + warp)) & 1u);
+#pragma unroll 1
+            for (int half = 0; half < kBatch / 32; ++half) {
+            uint32_t todo = __ballot_sync(0xffffffffu, (sm.list[k * kBatch + half * 32 + lane].y >> (28 + warp)) & 1u);
             while (todo) {
-                const int j = __ffs(todo) - 1;
+                const int j = half * 32 + __ffs(todo) - 1;
                 todo &= todo - 1;
-                const uint32_t e = sm.list[k * kChunk + j].x;
+                const uint32_t e = sm.list[k * kBatch + j].x;
                 const uint32_t zb = (e >> my_zshift) & 0xFu;
                 if ((e & my_xy) == my_xy && zb) {
                     const float4 *r4 = reinterpret_cast<const float4 *>(&sm.stage[slot][j * REC]);
@@ -258,6 +251,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                         }
                     }
                 }
+            }
             }
             __syncthreads();  // everyone is done with this ring slot before it is refilled
         }
@@ -313,6 +307,12 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                 }
             }
     }
+    // points that are not in canonical voxel order: exact per-point evaluation overwrites their rows
+    if (stray) {
+#pragma unroll
+        for (int v = 0; v < kVox; ++v)
+            if (vox_ok[v] && ((stray >> v) & 1u)) render_one_point<C, PROB>(p, n0 + v, px[v], py[v], pz[v]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -330,13 +330,14 @@ __global__ void __launch_bounds__(256) render_points_kernel(const RenderParams p
 // ------------------------------------------------------------------------------------------------
 int launch_render_tc(const RenderParams &rp, cudaStream_t stream);  // splat_forward_tc.cu
 
-// GF_B200_RENDER=simt selects the first-generation SIMT tile kernel (kept for A/B measurements);
-// the default is the tcgen05 kernel, which also handles non-canonical points inline.
+// Two tile kernels exist for canonical-order points.  The SIMT quad kernel (this file) is the default
+// because it is the faster one on B200 today (profiles/README.md); GF_B200_RENDER=tc selects the
+// tcgen05 kernel (splat_forward_tc.cu), kept for A/B measurements.  Both evaluate stray points inline.
 static bool use_simt_render() {
     static int cached = -1;
     if (cached < 0) {
         const char *e = getenv("GF_B200_RENDER");
-        cached = (e && e[0] == 's') ? 1 : 0;
+        cached = (e && e[0] == 't') ? 0 : 1;
     }
     return cached == 1;
 }
@@ -353,6 +354,7 @@ static int launch_render_t(const RenderParams &rp, bool tile_path, int num_sms, 
         render_tile_kernel<C, PROB><<<grid, kRenderThreads, smem, stream>>>(rp);
         GF_CUDA_TRY(cudaGetLastError());
         if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_after, stream));
+        return GF_OK;   // stray points were handled inside the tile kernel
     }
     const long long want = (static_cast<long long>(rp.d.N) + 255) / 256;
     const int grid = static_cast<int>(want < 8ll * num_sms ? (want > 0 ? want : 1) : 8ll * num_sms);

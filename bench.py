@@ -180,12 +180,18 @@ def main():
         ou = _lib.SplatOutputs(_ptr(o), None, None, None)
         calls.append((ins, ou, w))
     loss_buf = torch.zeros(1, device=dev)
+    pending = []
 
     def step(i):
         ins, ou, w = calls[i % N_SETS]
         _lib.check(L.gf_splat_forward(ctypes.byref(desc), ctypes.byref(ins), ctypes.byref(ou), _ptr(w), ws_bytes, sptr))
-        if world > 1:   # north star: NCCL only for the (scalar) loss all-reduce
-            dist.all_reduce(loss_buf)
+        if world > 1:
+            # north star: NCCL only for the (scalar) loss all-reduce.  It is issued asynchronously on
+            # NCCL's stream so that it overlaps the next sample's kernels; every handle is waited for
+            # before the timed region closes.
+            pending.append(dist.all_reduce(loss_buf, async_op=True))
+            if len(pending) > 8:
+                pending.pop(0).wait()
 
     def timed_region(nsteps, fn):
         if world > 1:
@@ -195,6 +201,8 @@ def main():
         e0.record(stream)
         for i in range(nsteps):
             fn(i)
+        while pending:
+            pending.pop(0).wait()
         e1.record(stream)
         torch.cuda.synchronize(dev)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)

@@ -364,8 +364,17 @@ def side_measurements(dev, kw, inp0, resident, desc):
                 cov6 = t["cov"].flatten(1)[:, [0, 4, 8, 1, 5, 2]]
                 return mod.local_aggregate(t["pts"], pi, t["means"], mi, t["opa"], t["sem"], radii, cov6,
                                            kw["H"], kw["W"], kw["D"])
-            out["ref_cuda_op"] = {"fwd_ms": timeit(ref_call, reps=10), "what": "reference localagg op call "
-                                  "(its Python prep + sort-based kernels) compiled for sm_100a, same GPU, same sample"}
+            ref_fwd = timeit(ref_call, reps=10)
+            R, logits, geom, binning, img = ref_call()
+            pi = ((t["pts"] - pc_min) / kw["grid_size"]).to(torch.int)
+            cov6 = t["cov"].flatten(1)[:, [0, 4, 8, 1, 5, 2]].contiguous()
+            g = torch.randn_like(logits)
+            ref_bwd = timeit(lambda: mod.local_aggregate_backward(geom, binning, img, kw["H"], kw["W"], kw["D"], R,
+                                                                  t["means"], t["pts"], pi, cov6, t["opa"], t["sem"], g),
+                             reps=3, warm=1)
+            out["ref_cuda_op"] = {"fwd_ms": ref_fwd, "bwd_ms": ref_bwd, "what": "reference localagg op "
+                                  "(its Python prep + sort-based kernels; backward = native call only) compiled for "
+                                  "sm_100a, same GPU, same sample"}
     except Exception as e:
         out["ref_cuda_op"] = {"error": repr(e)}
     return out

@@ -66,7 +66,7 @@ struct SplatWorkspace {
     size_t bytes;
 };
 
-constexpr int kPackThreads = 256;
+constexpr int kPackThreads = 64;   // small CTAs: ~400 of them cover the 148 SMs several times over
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

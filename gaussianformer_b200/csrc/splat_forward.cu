@@ -15,22 +15,29 @@ namespace gf {
 extern thread_local cudaEvent_t g_ev_before, g_ev_after;  // measurement hooks (cabi.cu)
 
 constexpr int kQuadSeg = 512;   // list entries resolved per segment
-constexpr int kBatch = 64;      // records staged per ring slot (two 32-record ballots per batch)
+constexpr int kBatch = 32;      // records staged per ring slot
+constexpr int kRing = 4;        // ring slots: a warp may run up to kRing-2 batches ahead of the slowest one
 
 template <int C>
 struct RenderSmem {
     static constexpr int REC = rec_floats(C);
-    alignas(128) float stage[2][kBatch * REC];
+    alignas(128) float stage[kRing][kBatch * REC];
     alignas(8) uint2 list[kQuadSeg + kBatch];  // x: box relative to the bin as bit masks, y: index | warp-hit bits
+    alignas(8) uint64_t bar_full[kRing];       // records of the slot have landed (128 cp.async arrivals)
+    alignas(8) uint64_t bar_empty[kRing];      // every warp is done with the slot (4 arrivals)
     int warp_count[2][kRenderThreads / 32];
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// the mbarrier receives one arrival from this thread when all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive_on(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_one(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // SIMT render kernel ("quad" kernel): bin = 8 x 4 columns x 16 z, one z-quad (4 voxels) per thread with
 // 4 x C accumulators in registers; a warp covers 4 x 4 x 8 voxels.
@@ -124,6 +131,17 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
         zsum[v] = 0.f; dens[v] = 0.f; keep[v] = 1.f;
     }
 
+    if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < kRing; ++r) {
+            mbar_init(&sm.bar_full[r], kRenderThreads);
+            mbar_init(&sm.bar_empty[r], kRenderThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    uint32_t gb = 0;   // batches consumed so far by this CTA: drives ring slots and barrier parities
+    // (the __syncthreads of Phase A below publishes the barrier initialisation)
+
     // ---- candidates: the ascending list of this bin's supertile ------------------------------------
     const int st_shift = 31 - __clz(p.st);
     const int s = (binX0 >> st_shift) * p.nsy + (binY0 >> st_shift);
@@ -133,6 +151,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
 
     int cpos = 0;
     while (cpos < ncand) {
+        __syncthreads();   // previous segment fully consumed (and, the first time, barriers initialised)
         // ======================= Phase A: ordered survivors of the box test ==========================
         int nlist = 0;
         while (cpos < ncand && nlist + kRenderThreads <= kQuadSeg) {
@@ -189,27 +208,32 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
         __syncthreads();
 
         // ======================= Phase B: stream records and accumulate ==============================
+        // No CTA-wide barrier in this loop: full[] / empty[] mbarriers let the four warps drift apart by
+        // up to kRing-2 batches, so a warp whose footprint is touched by few records does not wait.
         const int nchunks = (nlist + kBatch - 1) / kBatch;
-        auto issue = [&](int k) {  // all threads stage batch k into ring slot k&1: 64 records x 8 x 16 B = 512 copies
-            const int slot = k & 1;
+        auto issue = [&](int k, uint32_t b_index) {  // batch k of this segment -> ring slot b_index % kRing
+            const int slot = b_index % kRing;
+            const uint32_t use = b_index / kRing;
+            if (use > 0) mbar_wait(&sm.bar_empty[slot], (use - 1) & 1);   // previous occupant released by all warps
 #pragma unroll
-            for (int q = 0; q < kBatch * 8 / kRenderThreads; ++q) {
+            for (int q = 0; q < kBatch * 8 / kRenderThreads; ++q) {     // 32 records x 8 x 16 B = 256 copies
                 const int piece = tid + kRenderThreads * q, row = piece >> 3, col = (piece & 7) * 4;
                 if (k * kBatch + row < nlist) {
                     const uint32_t g = sm.list[k * kBatch + row].y & 0x0FFFFFFFu;
                     cp_async16(&sm.stage[slot][row * REC + col], p.records + static_cast<size_t>(g) * REC + col);
                 }
             }
-            cp_async_commit();
+            cp_async_arrive_on(&sm.bar_full[slot]);
         };
-        if (nchunks > 0) issue(0);
-        for (int k = 0; k < nchunks; ++k) {
-            const int slot = k & 1;
-            if (k + 1 < nchunks) { issue(k + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-            __syncthreads();   // batch k has landed for everybody
-            // records that touch my warp's footprint, in ascending order
 #pragma unroll 1
-            for (int half = 0; half < kBatch / 32; ++half) {
+        for (int k = 0; k < kRing - 1 && k < nchunks; ++k) issue(k, gb + k);
+#pragma unroll 1
+        for (int k = 0; k < nchunks; ++k, ++gb) {
+            const int slot = gb % kRing;
+            mbar_wait(&sm.bar_full[slot], (gb / kRing) & 1);
+            {
+            const int half = 0;
+            // records that touch my warp's footprint, in ascending order
             uint32_t todo = __ballot_sync(0xffffffffu, (sm.list[k * kBatch + half * 32 + lane].y >> (28 + warp)) & 1u);
             while (todo) {
                 const int j = half * 32 + __ffs(todo) - 1;
@@ -253,7 +277,9 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                 }
             }
             }
-            __syncthreads();  // everyone is done with this ring slot before it is refilled
+            __syncwarp();
+            if (lane == 0) mbar_arrive_one(&sm.bar_empty[slot]);       // my warp is done with this slot
+            if (k + kRing - 1 < nchunks) issue(k + kRing - 1, gb + kRing - 1);
         }
     }
 

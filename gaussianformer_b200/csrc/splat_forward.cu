@@ -245,23 +245,28 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                     const float4 g0 = r4[0], g1 = r4[1];
                     const float2 g2 = *reinterpret_cast<const float2 *>(r4 + 2);
                     float wv[kVox];
+                    // quadratic form on packed fp32 pairs: voxels (0,1) and (2,3) share each instruction
 #pragma unroll
-                    for (int v = 0; v < kVox; ++v) {
-                        const float dx = g0.x - px[v], dy = g0.y - py[v], dz = g0.z - pz[v];
-                        float t1 = g1.x * dx;
-                        t1 = fmaf(g1.w, dy, t1);
-                        t1 = fmaf(g2.y, dz, t1);
-                        float t2 = g1.y * dy;
-                        t2 = fmaf(g2.x, dz, t2);
-                        float q = t1 * dx;
-                        q = fmaf(t2, dy, q);
-                        q = fmaf(g1.z * dz, dz, q);
-                        const float E = ((zb >> v) & 1u) ? ex2_approx(q) : 0.f;
-                        wv[v] = g0.w * E;
+                    for (int h2 = 0; h2 < kVox / 2; ++h2) {
+                        const int v0 = 2 * h2, v1 = v0 + 1;
+                        const float2 dx = __fadd2_rn(make_float2(g0.x, g0.x), make_float2(-px[v0], -px[v1]));
+                        const float2 dy = __fadd2_rn(make_float2(g0.y, g0.y), make_float2(-py[v0], -py[v1]));
+                        const float2 dz = __fadd2_rn(make_float2(g0.z, g0.z), make_float2(-pz[v0], -pz[v1]));
+                        float2 t1 = __fmul2_rn(make_float2(g1.x, g1.x), dx);
+                        t1 = __ffma2_rn(make_float2(g1.w, g1.w), dy, t1);
+                        t1 = __ffma2_rn(make_float2(g2.y, g2.y), dz, t1);
+                        float2 t2 = __fmul2_rn(make_float2(g1.y, g1.y), dy);
+                        t2 = __ffma2_rn(make_float2(g2.x, g2.x), dz, t2);
+                        float2 q = __fmul2_rn(t1, dx);
+                        q = __ffma2_rn(t2, dy, q);
+                        q = __ffma2_rn(__fmul2_rn(make_float2(g1.z, g1.z), dz), dz, q);
+                        const float E0 = ((zb >> v0) & 1u) ? ex2_approx(q.x) : 0.f;
+                        const float E1 = ((zb >> v1) & 1u) ? ex2_approx(q.y) : 0.f;
+                        wv[v0] = g0.w * E0;
+                        wv[v1] = g0.w * E1;
                         if (PROB) {
-                            zsum[v] += wv[v];
-                            dens[v] += E;
-                            keep[v] *= (1.f - E);
+                            zsum[v0] += wv[v0]; dens[v0] += E0; keep[v0] *= (1.f - E0);
+                            zsum[v1] += wv[v1]; dens[v1] += E1; keep[v1] *= (1.f - E1);
                         }
                     }
 #pragma unroll

@@ -14,18 +14,22 @@ namespace gf {
 
 extern thread_local cudaEvent_t g_ev_before, g_ev_after;  // measurement hooks (cabi.cu)
 
+#ifndef GF_RENDER_VOX
+#define GF_RENDER_VOX 4   // voxels per thread of the tile kernel (2 or 4)
+#endif
 constexpr int kQuadSeg = 512;   // list entries resolved per segment
 constexpr int kBatch = 32;      // records staged per ring slot
 constexpr int kRing = 4;        // ring slots: a warp may run up to kRing-2 batches ahead of the slowest one
 
-template <int C>
+template <int C, int VOX>
 struct RenderSmem {
     static constexpr int REC = rec_floats(C);
+    static constexpr int NT = 512 / VOX;   // threads per CTA: 8 x 4 columns x (16 / VOX) z groups
     alignas(128) float stage[kRing][kBatch * REC];
     alignas(8) uint2 list[kQuadSeg + kBatch];  // x: box relative to the bin as bit masks, y: index | warp-hit bits
-    alignas(8) uint64_t bar_full[kRing];       // records of the slot have landed (128 cp.async arrivals)
-    alignas(8) uint64_t bar_empty[kRing];      // every warp is done with the slot (4 arrivals)
-    int warp_count[2][kRenderThreads / 32];
+    alignas(8) uint64_t bar_full[kRing];       // records of the slot have landed (one cp.async arrival per thread)
+    alignas(8) uint64_t bar_empty[kRing];      // every warp is done with the slot (one arrival per warp)
+    int warp_count[2][NT / 32];
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -39,51 +43,60 @@ __device__ __forceinline__ void mbar_arrive_one(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// SIMT render kernel ("quad" kernel): bin = 8 x 4 columns x 16 z, one z-quad (4 voxels) per thread with
-// 4 x C accumulators in registers; a warp covers 4 x 4 x 8 voxels.
+// SIMT render kernel: bin = 8 x 4 columns x 16 z, VOX consecutive z voxels per thread with VOX x C
+// accumulators in registers; a warp covers 4 x 4 columns x 2*VOX z.  VOX = 4: 128 threads, 128
+// registers, 4 CTAs per SM; VOX = 2: 256 threads, fewer registers per thread, more resident warps and
+// tighter warp footprints at the price of more per-record overhead.
 //   * Phase A resolves the bin's ordered Gaussian list; each entry carries the box clipped to the bin
 //     as bit masks (x: 8 bits, y: 4 bits, z: 16 bits) and one "this warp's footprint is touched" bit
 //     per warp, so Phase B never unpacks coordinates.
 //   * Phase B streams the records (cp.async, double buffered); every warp walks only the records that
 //     touch its footprint (ballot -> bit loop), a lane tests its column with one AND and its four
 //     voxels with one shift, and the class accumulation runs on packed fp32 pairs (FFMA2).
-template <int C, bool PROB>
-__global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kernel(const RenderParams p) {
+template <int C, bool PROB, int VOX>
+__global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : 4) : (PROB ? 2 : 3)) render_tile_kernel(const RenderParams p) {
+    constexpr int NT = 512 / VOX, NWARP = NT / 32;
+    constexpr uint32_t VMASK = (1u << VOX) - 1u;
     constexpr int REC = rec_floats(C);
     constexpr int CP2 = (C + 1) / 2;   // packed class pairs
     static_assert(REC == 32, "one record = 128 bytes");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    RenderSmem<C> &sm = *reinterpret_cast<RenderSmem<C> *>(smem_raw);
+    RenderSmem<C, VOX> &sm = *reinterpret_cast<RenderSmem<C, VOX> *>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.d.H, W = p.d.W, D = p.d.D;
 
     // ---- which voxels are mine -------------------------------------------------------------------
     const int binX0 = blockIdx.z * kBinX, binY0 = blockIdx.y * kBinY, binZ0 = blockIdx.x * kBinZ;
-    const int lx = (warp & 1) * 4 + (lane >> 3), ly = (lane >> 1) & 3, lq = (warp >> 1) * 2 + (lane & 1);  // quad 0..3
-    const int X = binX0 + lx, Y = binY0 + ly, Z0 = binZ0 + 4 * lq;
+    const int lx = (warp & 1) * 4 + (lane >> 3), ly = (lane >> 1) & 3, lq = (warp >> 1) * 2 + (lane & 1);  // z group
+    const int X = binX0 + lx, Y = binY0 + ly, Z0 = binZ0 + VOX * lq;
     const bool col_ok = X < H && Y < W;
     const long long n0 = (static_cast<long long>(X) * W + Y) * D + Z0;
-    const bool vec_ok = (D & 3) == 0;  // then n0 % 4 == 0 and Z0+3 < D whenever Z0 < D
+    const bool vec_ok = (D & 3) == 0;  // then n0 % VOX == 0 and Z0+VOX-1 < D whenever Z0 < D
 
-    float px[kVox], py[kVox], pz[kVox];
-    bool vox_ok[kVox];
+    float px[VOX], py[VOX], pz[VOX];
+    bool vox_ok[VOX];
 #pragma unroll
-    for (int v = 0; v < kVox; ++v) {
+    for (int v = 0; v < VOX; ++v) {
         vox_ok[v] = col_ok && (Z0 + v) < D;
         px[v] = py[v] = pz[v] = 0.f;
     }
     uint32_t stray = 0;   // bit v: point n0+v does not sit in voxel n0+v
     if (col_ok && Z0 < D) {
         if (vec_ok) {
-            const float4 *src = reinterpret_cast<const float4 *>(p.pts + 3 * n0);
-            const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-            px[0] = a.x; py[0] = a.y; pz[0] = a.z; px[1] = a.w;
-            py[1] = b.x; pz[1] = b.y; px[2] = b.z; py[2] = b.w;
-            pz[2] = c.x; px[3] = c.y; py[3] = c.z; pz[3] = c.w;
+            // 3*VOX contiguous floats, 8-byte aligned (n0 is even)
+            float raw[3 * VOX];
+            const float2 *src = reinterpret_cast<const float2 *>(p.pts + 3 * n0);
+#pragma unroll
+            for (int i = 0; i < 3 * VOX / 2; ++i) {
+                const float2 t = __ldg(src + i);
+                raw[2 * i] = t.x; raw[2 * i + 1] = t.y;
+            }
+#pragma unroll
+            for (int v = 0; v < VOX; ++v) { px[v] = raw[3 * v]; py[v] = raw[3 * v + 1]; pz[v] = raw[3 * v + 2]; }
         } else {
 #pragma unroll
-            for (int v = 0; v < kVox; ++v)
+            for (int v = 0; v < VOX; ++v)
                 if (vox_ok[v]) {
                     px[v] = __ldg(p.pts + 3 * (n0 + v));
                     py[v] = __ldg(p.pts + 3 * (n0 + v) + 1);
@@ -94,7 +107,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
         // point that is not within 1e-3 cells of a voxel face; only those pay the exact IEEE divisions.
         const float inv = __frcp_rn(p.d.grid_size);
 #pragma unroll
-        for (int v = 0; v < kVox; ++v)
+        for (int v = 0; v < VOX; ++v)
             if (vox_ok[v]) {
                 int ix, iy, iz;
                 if (p.points_int) {
@@ -120,12 +133,12 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
     }
     // entry word: x mask [0,8) | y mask [8,12) | z mask [16,32)
     const uint32_t my_xy = (1u << lx) | (1u << (8 + ly));
-    const int my_zshift = 16 + 4 * lq;
+    const int my_zshift = 16 + VOX * lq;
 
-    float2 acc[kVox][CP2];
-    float zsum[kVox], dens[kVox], keep[kVox];
+    float2 acc[VOX][CP2];
+    float zsum[VOX], dens[VOX], keep[VOX];
 #pragma unroll
-    for (int v = 0; v < kVox; ++v) {
+    for (int v = 0; v < VOX; ++v) {
 #pragma unroll
         for (int c = 0; c < CP2; ++c) acc[v][c] = make_float2(0.f, 0.f);
         zsum[v] = 0.f; dens[v] = 0.f; keep[v] = 1.f;
@@ -134,8 +147,8 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
     if (tid == 0) {
 #pragma unroll
         for (int r = 0; r < kRing; ++r) {
-            mbar_init(&sm.bar_full[r], kRenderThreads);
-            mbar_init(&sm.bar_empty[r], kRenderThreads / 32);
+            mbar_init(&sm.bar_full[r], NT);
+            mbar_init(&sm.bar_empty[r], NWARP);
         }
         mbar_fence_init();
     }
@@ -154,13 +167,13 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
         __syncthreads();   // previous segment fully consumed (and, the first time, barriers initialised)
         // ======================= Phase A: ordered survivors of the box test ==========================
         int nlist = 0;
-        while (cpos < ncand && nlist + kRenderThreads <= kQuadSeg) {
+        while (cpos < ncand && nlist + NT <= kQuadSeg) {
             constexpr int kPre = 4;   // rounds fetched together (memory-level parallelism)
             int gg[kPre];
             uint4 bb[kPre];
 #pragma unroll
             for (int u = 0; u < kPre; ++u) {
-                const int i = cpos + u * kRenderThreads + tid;
+                const int i = cpos + u * NT + tid;
                 gg[u] = i < ncand ? __ldg(cand + i) : -1;
             }
 #pragma unroll
@@ -168,7 +181,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                 bb[u] = gg[u] >= 0 ? __ldg(reinterpret_cast<const uint4 *>(p.boxes) + gg[u]) : make_uint4(1u, 1u, 1u, 1u);
 #pragma unroll
             for (int u = 0; u < kPre; ++u) {
-                if (cpos >= ncand || nlist + kRenderThreads > kQuadSeg) break;   // uniform
+                if (cpos >= ncand || nlist + NT > kQuadSeg) break;   // uniform
                 const uint4 b = bb[u];
                 const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16,
                                z0 = b.z & 0xffffu, z1 = b.z >> 16;
@@ -184,22 +197,22 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                 // which warp footprints (x half, z half) does the clipped box touch?
                 uint32_t wh = 0;
 #pragma unroll
-                for (int wq = 0; wq < 4; ++wq)
-                    if ((xm & (0xFu << (4 * (wq & 1)))) && (zm & (0xFFu << (8 * (wq >> 1))))) wh |= 1u << wq;
-                const uint2 entry = make_uint2(xm | (ym << 8) | (zm << 16), static_cast<uint32_t>(gg[u]) | (wh << 28));
+                for (int wq = 0; wq < NWARP; ++wq)
+                    if ((xm & (0xFu << (4 * (wq & 1)))) && (zm & (((1u << (2 * VOX)) - 1u) << (2 * VOX * (wq >> 1))))) wh |= 1u << wq;
+                const uint2 entry = make_uint2(xm | (ym << 8) | (zm << 16), static_cast<uint32_t>(gg[u]) | (wh << 24));
                 const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
                 if (lane == 0) sm.warp_count[u & 1][warp] = __popc(ballot);
                 __syncthreads();
                 int off = nlist, total = 0;
 #pragma unroll
-                for (int k = 0; k < kRenderThreads / 32; ++k) {
+                for (int k = 0; k < NT / 32; ++k) {
                     const int c = sm.warp_count[u & 1][k];
                     if (k < warp) off += c;
                     total += c;
                 }
                 if (hit) sm.list[off + __popc(ballot & lanemask_lt())] = entry;
                 nlist += total;
-                cpos += kRenderThreads;
+                cpos += NT;
             }
             __syncthreads();
         }
@@ -216,10 +229,10 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
             const uint32_t use = b_index / kRing;
             if (use > 0) mbar_wait(&sm.bar_empty[slot], (use - 1) & 1);   // previous occupant released by all warps
 #pragma unroll
-            for (int q = 0; q < kBatch * 8 / kRenderThreads; ++q) {     // 32 records x 8 x 16 B = 256 copies
-                const int piece = tid + kRenderThreads * q, row = piece >> 3, col = (piece & 7) * 4;
-                if (k * kBatch + row < nlist) {
-                    const uint32_t g = sm.list[k * kBatch + row].y & 0x0FFFFFFFu;
+            for (int q = 0; q < (kBatch * 8 + NT - 1) / NT; ++q) {     // 32 records x 8 x 16 B = 256 copies
+                const int piece = tid + NT * q, row = piece >> 3, col = (piece & 7) * 4;
+                if (piece < kBatch * 8 && k * kBatch + row < nlist) {
+                    const uint32_t g = sm.list[k * kBatch + row].y & 0x00FFFFFFu;
                     cp_async16(&sm.stage[slot][row * REC + col], p.records + static_cast<size_t>(g) * REC + col);
                 }
             }
@@ -234,20 +247,20 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
             {
             const int half = 0;
             // records that touch my warp's footprint, in ascending order
-            uint32_t todo = __ballot_sync(0xffffffffu, (sm.list[k * kBatch + half * 32 + lane].y >> (28 + warp)) & 1u);
+            uint32_t todo = __ballot_sync(0xffffffffu, (sm.list[k * kBatch + half * 32 + lane].y >> (24 + warp)) & 1u);
             while (todo) {
                 const int j = half * 32 + __ffs(todo) - 1;
                 todo &= todo - 1;
                 const uint32_t e = sm.list[k * kBatch + j].x;
-                const uint32_t zb = (e >> my_zshift) & 0xFu;
+                const uint32_t zb = (e >> my_zshift) & VMASK;
                 if ((e & my_xy) == my_xy && zb) {
                     const float4 *r4 = reinterpret_cast<const float4 *>(&sm.stage[slot][j * REC]);
                     const float4 g0 = r4[0], g1 = r4[1];
                     const float2 g2 = *reinterpret_cast<const float2 *>(r4 + 2);
-                    float wv[kVox];
+                    float wv[VOX];
                     // quadratic form on packed fp32 pairs: voxels (0,1) and (2,3) share each instruction
 #pragma unroll
-                    for (int h2 = 0; h2 < kVox / 2; ++h2) {
+                    for (int h2 = 0; h2 < VOX / 2; ++h2) {
                         const int v0 = 2 * h2, v1 = v0 + 1;
                         const float2 dx = __fadd2_rn(make_float2(g0.x, g0.x), make_float2(-px[v0], -px[v1]));
                         const float2 dy = __fadd2_rn(make_float2(g0.y, g0.y), make_float2(-py[v0], -py[v1]));
@@ -273,7 +286,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
                     for (int c4 = 0; c4 < (C + 3) / 4; ++c4) {
                         const float4 s4 = r4[3 + c4];
 #pragma unroll
-                        for (int v = 0; v < kVox; ++v) {
+                        for (int v = 0; v < VOX; ++v) {
                             const float2 ww = make_float2(wv[v], wv[v]);
                             acc[v][2 * c4] = __ffma2_rn(make_float2(s4.x, s4.y), ww, acc[v][2 * c4]);
                             if (2 * c4 + 1 < CP2) acc[v][2 * c4 + 1] = __ffma2_rn(make_float2(s4.z, s4.w), ww, acc[v][2 * c4 + 1]);
@@ -290,14 +303,14 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
 
     // ---- epilogue ----------------------------------------------------------------------------------
     if (!(col_ok && Z0 < D)) return;
-    float out[kVox][C];
+    float out[VOX][C];
 #pragma unroll
-    for (int v = 0; v < kVox; ++v)
+    for (int v = 0; v < VOX; ++v)
 #pragma unroll
         for (int c = 0; c < C; ++c) out[v][c] = (c & 1) ? acc[v][c >> 1].y : acc[v][c >> 1].x;
     if (PROB) {
 #pragma unroll
-        for (int v = 0; v < kVox; ++v) {
+        for (int v = 0; v < VOX; ++v) {
             if (zsum[v] > 1e-9f) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) out[v][c] = __fdiv_rn(out[v][c], zsum[v]);
@@ -309,25 +322,33 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
     }
     float *dst = p.out.logits + n0 * C;
     if (vec_ok) {
-        float flat[kVox * C];
+        float flat[VOX * C];
 #pragma unroll
-        for (int v = 0; v < kVox; ++v)
+        for (int v = 0; v < VOX; ++v)
 #pragma unroll
             for (int c = 0; c < C; ++c) flat[v * C + c] = out[v][c];
 #pragma unroll
-        for (int i = 0; i < kVox * C / 4; ++i)
-            __stcs(reinterpret_cast<float4 *>(dst) + i,
-                   make_float4(flat[4 * i], flat[4 * i + 1], flat[4 * i + 2], flat[4 * i + 3]));
+        if constexpr ((VOX * C) % 4 == 0) {      // n0 * C * 4 bytes is then a multiple of 16
+#pragma unroll
+            for (int i = 0; i < VOX * C / 4; ++i)
+                __stcs(reinterpret_cast<float4 *>(dst) + i,
+                       make_float4(flat[4 * i], flat[4 * i + 1], flat[4 * i + 2], flat[4 * i + 3]));
+        } else {                                  // n0 is even, so rows start 8-byte aligned
+#pragma unroll
+            for (int i = 0; i < VOX * C / 2; ++i)
+                __stcs(reinterpret_cast<float2 *>(dst) + i, make_float2(flat[2 * i], flat[2 * i + 1]));
+        }
         if (PROB) {
-            __stcs(reinterpret_cast<float4 *>(p.out.bin_logits + n0),
-                   make_float4(1.f - keep[0], 1.f - keep[1], 1.f - keep[2], 1.f - keep[3]));
-            __stcs(reinterpret_cast<float4 *>(p.out.density + n0), make_float4(dens[0], dens[1], dens[2], dens[3]));
-            __stcs(reinterpret_cast<float4 *>(p.out.probability + n0),
-                   make_float4(zsum[0], zsum[1], zsum[2], zsum[3]));
+#pragma unroll
+            for (int v = 0; v < VOX; v += 2) {
+                __stcs(reinterpret_cast<float2 *>(p.out.bin_logits + n0 + v), make_float2(1.f - keep[v], 1.f - keep[v + 1]));
+                __stcs(reinterpret_cast<float2 *>(p.out.density + n0 + v), make_float2(dens[v], dens[v + 1]));
+                __stcs(reinterpret_cast<float2 *>(p.out.probability + n0 + v), make_float2(zsum[v], zsum[v + 1]));
+            }
         }
     } else {
 #pragma unroll
-        for (int v = 0; v < kVox; ++v)
+        for (int v = 0; v < VOX; ++v)
             if (vox_ok[v]) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) dst[v * C + c] = out[v][c];
@@ -341,7 +362,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : 4) render_tile_kern
     // points that are not in canonical voxel order: exact per-point evaluation overwrites their rows
     if (stray) {
 #pragma unroll
-        for (int v = 0; v < kVox; ++v)
+        for (int v = 0; v < VOX; ++v)
             if (vox_ok[v] && ((stray >> v) & 1u)) render_one_point<C, PROB>(p, n0 + v, px[v], py[v], pz[v]);
     }
 }
@@ -373,16 +394,28 @@ static bool use_simt_render() {
     return cached == 1;
 }
 
+// voxels per thread of the tile kernel: GF_B200_VOX=2|4 overrides the default
+static int render_vox() {
+    static int cached = 0;
+    if (cached == 0) {
+        const char *e = getenv("GF_B200_VOX");
+        cached = (e && e[0] == '2') ? 2 : GF_RENDER_VOX;
+    }
+    return cached;
+}
+
 template <int C, bool PROB>
 static int launch_render_t(const RenderParams &rp, bool tile_path, int num_sms, cudaStream_t stream) {
     if (tile_path && !use_simt_render()) return launch_render_tc(rp, stream);
     if (tile_path) {
-        const size_t smem = sizeof(RenderSmem<C>);
         const int nbx = (rp.d.H + kBinX - 1) / kBinX;
         GF_REQUIRE(rp.nby <= 65535 && nbx <= 65535, GF_ERR_UNSUPPORTED, "splat: grid too large for the render launch");
         const dim3 grid(rp.nzc, rp.nby, nbx);
         if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_before, stream));
-        render_tile_kernel<C, PROB><<<grid, kRenderThreads, smem, stream>>>(rp);
+        if (render_vox() == 2)
+            render_tile_kernel<C, PROB, 2><<<grid, 256, sizeof(RenderSmem<C, 2>), stream>>>(rp);
+        else
+            render_tile_kernel<C, PROB, 4><<<grid, 128, sizeof(RenderSmem<C, 4>), stream>>>(rp);
         GF_CUDA_TRY(cudaGetLastError());
         if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_after, stream));
         return GF_OK;   // stray points were handled inside the tile kernel

@@ -10,8 +10,8 @@ Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md "
 
 * value        whole-job Gaussians/s with inputs resident in HBM, CUDA-event timed, max over ranks
 * e2e          the same metric through the public module (`local_aggregate.LocalAggregator`) with
-               HOST (pinned) inputs: H2D of every input + forward + argmax + D2H of the occupancy
-               prediction inside the timed region
+               HOST (pinned) inputs: H2D of every input + forward (logits + fused arg-max) + D2H of
+               the occupancy prediction inside the timed region
 * roofline     the tile render kernel timed alone (events recorded around it inside the C ABI),
                algorithmic bytes 112*G + 84*N   over the measured HBM copy peak
 * cpu_baseline the oracle's C/OpenMP port of the reference algorithm on the host cores (rank 0)
@@ -177,7 +177,7 @@ def main():
     for t, o, w in zip(sets, outs, wss):
         ins = _lib.SplatInputs(_ptr(t["pts"]), None, _ptr(t["means"]), None, _ptr(t["opa"]), _ptr(t["sem"]),
                                _ptr(t["cov"]), None, _ptr(t["scales"]))
-        ou = _lib.SplatOutputs(_ptr(o), None, None, None)
+        ou = _lib.SplatOutputs(_ptr(o), None, None, None, None)
         calls.append((ins, ou, w))
     loss_buf = torch.zeros(1, device=dev)
     pending = []
@@ -253,8 +253,8 @@ def main():
     def e2e_step(i):
         hin = host[i % 2]
         d = {k: v.to(dev, non_blocking=True) for k, v in hin.items()}
-        logits = module(d["pts"], d["means"], d["opa"], d["sem"], d["scales"], d["cov"])
-        pred_host.copy_(logits.argmax(dim=1).to(torch.uint8), non_blocking=True)
+        _logits, occ = module.forward_with_occupancy(d["pts"], d["means"], d["opa"], d["sem"], d["scales"], d["cov"])
+        pred_host.copy_(occ, non_blocking=True)
         if world > 1:
             dist.all_reduce(loss_buf)
         stream.synchronize()        # the caller consumes the prediction on the host every step
@@ -271,7 +271,7 @@ def main():
     e2e_ms = max(e2e_ms_dev, 0.0) / e2e_steps
     e2e = {"value": world * G_COUNTED / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall * 1e3 / e2e_steps,
-           "api": "local_aggregate.LocalAggregator.forward (validate=False) + argmax"}
+           "api": "local_aggregate.LocalAggregator.forward_with_occupancy (validate=False): logits + fused arg-max"}
 
     extras = {}
     if rank == 0 and not args.no_extras:

@@ -41,7 +41,8 @@ class SplatInputs(Structure):
 
 
 class SplatOutputs(Structure):
-    _fields_ = [("logits", c_void_p), ("bin_logits", c_void_p), ("density", c_void_p), ("probability", c_void_p)]
+    _fields_ = [("logits", c_void_p), ("bin_logits", c_void_p), ("density", c_void_p), ("probability", c_void_p),
+                ("argmax", c_void_p)]
 
 
 class SplatGrads(Structure):

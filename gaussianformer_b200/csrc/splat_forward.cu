@@ -320,6 +320,18 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : 4) : (PROB ?
             }
         }
     }
+    if (p.out.argmax) {   // fused occupancy prediction (lowest index on ties)
+        uint32_t packed = 0;
+#pragma unroll
+        for (int v = 0; v < VOX; ++v) packed |= static_cast<uint32_t>(argmax_of<C>(out[v])) << (8 * v);
+        if (vec_ok && VOX == 4) {
+            *reinterpret_cast<uint32_t *>(p.out.argmax + n0) = packed;
+        } else {
+#pragma unroll
+            for (int v = 0; v < VOX; ++v)
+                if (vox_ok[v]) p.out.argmax[n0 + v] = static_cast<uint8_t>(packed >> (8 * v));
+        }
+    }
     float *dst = p.out.logits + n0 * C;
     if (vec_ok) {
         float flat[VOX * C];

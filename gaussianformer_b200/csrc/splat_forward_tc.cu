@@ -428,6 +428,14 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
                 p.out.density[n] = dens;
                 p.out.probability[n] = zsum;
             }
+            if (p.out.argmax) {
+                int best = 0;
+                float bv = acc[0];
+#pragma unroll
+                for (int c = 1; c < C; ++c)
+                    if (acc[c] > bv) { bv = acc[c]; best = c; }
+                p.out.argmax[n] = static_cast<uint8_t>(best);
+            }
             if ((C & 1) == 0) {
 #pragma unroll
                 for (int c = 0; c < C; c += 2) __stcs(reinterpret_cast<float2 *>(dst + c), make_float2(acc[c], acc[c + 1]));

@@ -21,6 +21,17 @@ struct RenderParams {
     int nzc;         // z chunks
 };
 
+// index of the largest of C values, lowest index on ties
+template <int C>
+__device__ __forceinline__ int argmax_of(const float (&v)[C]) {
+    int best = 0;
+    float bv = v[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c)
+        if (v[c] > bv) { bv = v[c]; best = c; }
+    return best;
+}
+
 // Evaluate point n = (x,y,z) against the ascending Gaussian list of its supertile with the exact
 // integer-box test and write its output row(s).  Follows FORWARD::renderCUDA
 // (model/head/localagg/src/forward.cu:46-82; prob: localagg_prob/src/forward.cu:56-101).
@@ -97,6 +108,7 @@ __device__ __forceinline__ void render_one_point(const RenderParams &p, long lon
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) p.out.logits[n * C + c] = acc[c];
+    if (p.out.argmax) p.out.argmax[n] = static_cast<uint8_t>(argmax_of<C>(acc));
 }
 
 }  // namespace gf

@@ -54,8 +54,10 @@ def _require_cuda(*tensors):
                 "gaussianformer_b200 ops are CUDA-only (sm_100a); got a CPU tensor. There is no CPU fallback.")
 
 
-def splat_forward_raw(desc, pts, means, opa, sem, cov, *, points_int=None, means_int=None, radii=None, scales=None):
-    """One sample through ``gf_splat_forward``.  Returns (outputs tuple, workspace tensor)."""
+def splat_forward_raw(desc, pts, means, opa, sem, cov, *, points_int=None, means_int=None, radii=None, scales=None,
+                      argmax_out=None):
+    """One sample through ``gf_splat_forward``.  Returns (outputs tuple, workspace tensor).
+    ``argmax_out``: optional uint8 ``[N]`` tensor that receives the fused arg-max class."""
     L = _lib.lib()
     dev = pts.device
     with torch.cuda.device(dev):
@@ -73,7 +75,7 @@ def splat_forward_raw(desc, pts, means, opa, sem, cov, *, points_int=None, means
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         ins = SplatInputs(_ptr(pts), _ptr(points_int), _ptr(means), _ptr(means_int), _ptr(opa), _ptr(sem), _ptr(cov),
                           _ptr(radii), _ptr(scales))
-        outs = SplatOutputs(_ptr(logits), _ptr(binl), _ptr(dens), _ptr(probability))
+        outs = SplatOutputs(_ptr(logits), _ptr(binl), _ptr(dens), _ptr(probability), _ptr(argmax_out))
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(L.gf_splat_forward(ctypes.byref(desc), ctypes.byref(ins), ctypes.byref(outs), _ptr(ws), ws_bytes,
                                       stream))
@@ -217,6 +219,26 @@ class LocalAggregator(_LocalAggregatorBase):
         outs = self._run(pts, means3D, opacities, semantics, scales, cov3D)
         assert not self.inv_softmax  # the reference's `assert False` branch
         return outs[0] if len(outs) == 1 else torch.stack(outs, 0)
+
+
+    @torch.no_grad()
+    def forward_with_occupancy(self, pts, means3D, opacities, semantics, scales, cov3D):
+        """Inference helper beyond the reference API: returns ``(logits [N,C], occ [N] uint8)`` with
+        ``occ == logits.argmax(1)`` computed in the render epilogue (what ``GaussianHead.forward`` does
+        next, model/head/gaussian_head.py:185), so the logits are not re-read.  Batch of 1."""
+        _require_cuda(pts, means3D, opacities, semantics, scales, cov3D)
+        assert pts.shape[0] == 1
+        cfg = self._cfg()
+        desc = _make_desc(means3D.shape[1], pts.shape[1], semantics.shape[2], cfg["H"], cfg["W"], cfg["D"],
+                          cfg["variant"], cfg["radii_axes"], 9, cfg["pc_min"], cfg["grid_size"],
+                          cfg["scale_multiplier"], cfg["radii_min"])
+        occ = torch.empty(pts.shape[1], dtype=torch.uint8, device=pts.device)
+        (logits, _, _, _), ws = splat_forward_raw(desc, _f32c(pts[0]), _f32c(means3D[0]), _f32c(opacities[0]),
+                                                 _f32c(semantics[0]), _f32c(cov3D[0]).reshape(-1, 9),
+                                                 scales=_f32c(scales[0]), argmax_out=occ)
+        if self.validate:
+            _assert_flags(read_flags(ws, pts.device))
+        return logits, occ
 
 
 class LocalAggregatorProb(_LocalAggregatorBase):

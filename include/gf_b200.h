@@ -97,6 +97,9 @@ typedef struct gf_splat_outputs {
     float *bin_logits;  /* [N]  (prob only) */
     float *density;     /* [N]  (prob only) */
     float *probability; /* [N]  (prob only; saved for backward like the reference) */
+    uint8_t *argmax;    /* [N]  optional, NULL = off: class with the largest logit per point (lowest
+                           index on ties) — the `argmax(dim=1)` of GaussianHead.forward
+                           (model/head/gaussian_head.py:185) fused into the render epilogue */
 } gf_splat_outputs;
 
 typedef struct gf_splat_grads {

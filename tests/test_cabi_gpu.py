@@ -50,7 +50,7 @@ def test_status_codes():
     assert b"C=7" in L.gf_last_error()
     t = torch.zeros(64, device="cuda")
     ins = _lib.SplatInputs(*([ctypes.c_void_p(t.data_ptr())] * 9))
-    outs = _lib.SplatOutputs(*([ctypes.c_void_p(t.data_ptr())] * 4))
+    outs = _lib.SplatOutputs(*([ctypes.c_void_p(t.data_ptr())] * 5))
     rc = L.gf_splat_forward(ctypes.byref(d), ctypes.byref(ins), ctypes.byref(outs), ctypes.c_void_p(t.data_ptr()), 16, None)
     assert rc == 2                                                                        # GF_ERR_WORKSPACE
     assert 18 in _lib.supported_classes()

@@ -170,3 +170,22 @@ def test_vs_reference_goldens(fixture, cfg, seed, perturb, per_axis):
                             ("sem", t["sem"].grad[0], gold["semantics_grad"]),
                             ("cov", t["cov"].grad[0], oracle.cov6_grad_to_3x3(gold["cov_grad"]))):
         h.assert_close(mine.cpu().numpy(), ref, rtol=2e-3, atol=5 * h.grad_tolerance(ref), what="grad %s vs reference op" % name)
+
+
+def test_fused_argmax_matches_logits():
+    kw, inp, variant = h.splat_case("gs25600_solid", 2, True, dict(G=2000))
+    m = h.make_module(kw, variant)
+    t = h.to_dev(inp)
+    logits, occ = m.forward_with_occupancy(t["pts"], t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
+    ref = m(t["pts"], t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
+    assert torch.equal(logits, ref)
+    assert occ.dtype == torch.uint8 and occ.shape == (logits.shape[0],)
+    picked = logits.gather(1, occ.long()[:, None])[:, 0]
+    assert torch.equal(picked, logits.max(dim=1).values)          # a maximiser ...
+    first = (logits == logits.max(dim=1, keepdim=True).values).float().argmax(dim=1)
+    assert torch.equal(occ.long(), first)                          # ... and the lowest-index one
+    # stray points (permuted order) go through the per-point path and must report their arg-max too
+    perm = torch.randperm(t["pts"].shape[1], generator=torch.Generator().manual_seed(0)).cuda()
+    lg2, occ2 = m.forward_with_occupancy(t["pts"][:, perm].contiguous(), t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
+    first2 = (lg2 == lg2.max(dim=1, keepdim=True).values).float().argmax(dim=1)
+    assert torch.equal(occ2.long(), first2)

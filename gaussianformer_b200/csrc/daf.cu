@@ -83,7 +83,7 @@ template <> struct Vec<1> {
 // VEC = 4: C % 128 == 0 and (C/Gr)/4 a power of two <= 32 (a group is a run of whole lanes).
 // VEC = 1: any C, Gr.
 template <int VEC, bool BACKWARD>
-__global__ void __launch_bounds__(kDafThreads) daf_kernel(const DafParams p) {
+__global__ void __launch_bounds__(kDafThreads, 3) daf_kernel(const DafParams p) {
     using V = Vec<VEC>;
     using T = typename V::T;
     const int lane = threadIdx.x & 31;
@@ -91,10 +91,14 @@ __global__ void __launch_bounds__(kDafThreads) daf_kernel(const DafParams p) {
     const int gdim = C / Gr;
     const long long npts = static_cast<long long>(p.d.batch) * p.d.num_pts;
     const long long warps = static_cast<long long>(gridDim.x) * (kDafThreads / 32);
-    int lh[kMaxLevels], lw[kMaxLevels], ls[kMaxLevels];
-#pragma unroll
-    for (int l = 0; l < kMaxLevels; ++l)
-        if (l < L) { lh[l] = p.shape[2 * l]; lw[l] = p.shape[2 * l + 1]; ls[l] = p.start[l]; }
+    // level table in shared memory (dynamically indexed registers would spill to local memory)
+    __shared__ int lh[kMaxLevels], lw[kMaxLevels], ls[kMaxLevels];
+    if (threadIdx.x < L) {
+        lh[threadIdx.x] = p.shape[2 * threadIdx.x];
+        lw[threadIdx.x] = p.shape[2 * threadIdx.x + 1];
+        ls[threadIdx.x] = p.start[threadIdx.x];
+    }
+    __syncthreads();
 
     for (long long bp = static_cast<long long>(blockIdx.x) * (kDafThreads / 32) + (threadIdx.x >> 5); bp < npts; bp += warps) {
         const int b = static_cast<int>(bp / p.d.num_pts);

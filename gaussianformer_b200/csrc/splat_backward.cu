@@ -26,6 +26,7 @@ struct BwdParams {
     int32_t *v2p;      // [H*W*D]
     int32_t *big_list; // [G]
     int32_t *big_count;
+    float4 *aux;       // [N] prob only: per-point terms that do not depend on the Gaussian
 };
 
 __global__ void __launch_bounds__(256) voxel_map_kernel(const BwdParams p) {
@@ -42,6 +43,22 @@ __global__ void __launch_bounds__(256) voxel_map_kernel(const BwdParams p) {
         }
         if (ix < 0 || ix >= H || iy < 0 || iy >= W || iz < 0 || iz >= D) continue;
         atomicMax(p.v2p + (static_cast<long long>(ix) * W + iy) * D + iz, static_cast<int>(n));
+    }
+}
+
+// Prob variant: everything in localagg_prob/src/backward.cu:76-100 that depends on the point only is
+// folded into one float4 per point, read once per (Gaussian, point) pair instead of 2C+4 scalars:
+//   x = sum_k dL/dlogits[n,k] * logits[n,k]     (so that sum_k up_k (sem_k - logits_k) = up.sem - x)
+//   y = (1 - bin_logits[n]) * dL/dbin[n]
+//   z = dL/ddensity[n]
+//   w = 1 / probability[n]  if probability[n] > 1e-9 else 0   (0 switches the logits branch off)
+__global__ void __launch_bounds__(256) prob_aux_kernel(const BwdParams p, int C) {
+    for (long long n = blockIdx.x * 256ll + threadIdx.x; n < p.d.N; n += 256ll * gridDim.x) {
+        float x = 0.f;
+        for (int k = 0; k < C; ++k) x = fmaf(__ldg(p.gr.logits_grad + n * C + k), __ldg(p.gr.logits + n * C + k), x);
+        const float Z = __ldg(p.gr.probability + n);
+        p.aux[n] = make_float4(x, (1.f - __ldg(p.gr.bin_logits + n)) * __ldg(p.gr.bin_logits_grad + n),
+                               __ldg(p.gr.density_grad + n), Z > 1e-9f ? __fdiv_rn(1.f, Z) : 0.f);
     }
 }
 
@@ -118,26 +135,22 @@ struct GaussAcc {
             so += t;
             w = opa * t;
         } else {
-            // localagg_prob/src/backward.cu:76-100
-            const float Z = __ldg(p.gr.probability + n);
+            // localagg_prob/src/backward.cu:76-100 with the point-only terms pre-folded (prob_aux_kernel)
+            const float4 ax = __ldg(p.aux + n);
             const float Pt = norm * E;
             float pi = 0.f;
-            if (Z > 1e-9f) {
-                float u = 0.f;
-                const float inv = __fdiv_rn(1.f, Z);
-                const float sfac = Pt * opa * inv;
+            if (ax.w > 0.f) {
+                float u = -ax.x;
+                const float sfac = Pt * opa * ax.w;
 #pragma unroll
                 for (int k = 0; k < C; ++k) {
-                    const float lg = __ldg(p.gr.logits + n * C + k);
-                    u = fmaf(up[k], sem[k] - lg, u);
+                    u = fmaf(up[k], sem[k], u);
                     ss[k] = fmaf(up[k], sfac, ss[k]);
                 }
-                pi = u * opa * inv;
-                so = fmaf(u * Pt, inv, so);
+                pi = u * opa * ax.w;
+                so = fmaf(u * Pt, ax.w, so);
             }
-            const float eps = pi * norm +
-                              __fdiv_rn(1.f - __ldg(p.gr.bin_logits + n), 1.f - E + 1e-9f) * __ldg(p.gr.bin_logits_grad + n) +
-                              __ldg(p.gr.density_grad + n);
+            const float eps = pi * norm + __fdiv_rn(ax.y, 1.f - E + 1e-9f) + ax.z;
             sg += __fdiv_rn(pi * Pt * 0.5f, det);
             w = eps * E;
         }
@@ -334,6 +347,7 @@ __global__ void __launch_bounds__(kBwdThreads) backward_big_kernel(const BwdPara
 // ------------------------------------------------------------------------------------------------
 struct BwdWorkspace {
     int32_t *v2p, *big_list, *big_count;
+    float4 *aux;
     size_t bytes;
 };
 
@@ -350,6 +364,7 @@ void plan_backward_workspace(const gf_splat_desc &d, void *base, BwdWorkspace *w
     ws->big_count = reinterpret_cast<int32_t *>(take(64));
     ws->v2p = reinterpret_cast<int32_t *>(take(size_t(d.H) * d.W * d.D * 4));
     ws->big_list = reinterpret_cast<int32_t *>(take(size_t(d.G) * 4));
+    ws->aux = reinterpret_cast<float4 *>(take(d.variant == GF_SPLAT_PROB ? size_t(d.N) * 16 : 0));
     ws->bytes = off;
 }
 
@@ -367,6 +382,10 @@ static int launch_backward_t(const BwdParams &bp, int num_sms, cudaStream_t stre
     const int grid0 = static_cast<int>(want < 16ll * num_sms ? (want > 0 ? want : 1) : 16ll * num_sms);
     voxel_map_kernel<<<grid0, 256, 0, stream>>>(bp);
     GF_CUDA_TRY(cudaGetLastError());
+    if (PROB) {
+        prob_aux_kernel<<<grid0, 256, 0, stream>>>(bp, C);
+        GF_CUDA_TRY(cudaGetLastError());
+    }
     const int per_cta = kBwdThreads / 32;
     backward_small_kernel<C, PROB><<<(d.G + per_cta - 1) / per_cta, kBwdThreads, 0, stream>>>(bp);
     GF_CUDA_TRY(cudaGetLastError());
@@ -386,6 +405,7 @@ int launch_backward(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_
     bp.v2p = ws.v2p;
     bp.big_list = ws.big_list;
     bp.big_count = ws.big_count;
+    bp.aux = ws.aux;
     const bool prob = d.variant == GF_SPLAT_PROB;
 #define GF_CASE(CC)                                                       \
     case CC:                                                              \

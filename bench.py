@@ -241,27 +241,49 @@ def main():
                 "traffic": traffic, "kernel": "render_tc_kernel<18,false>" if os.environ.get("GF_B200_RENDER", "")[:1] == "t" else "render_tile_kernel<18,false>", "kernel_ms": render_ms,
                 "algorithmic_bytes": alg, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)"}
 
-    # ---- e2e: public module, host (pinned) inputs, H2D + forward + argmax + D2H -------------------
+    # ---- e2e: public module, HOST inputs: H2D + forward (logits + fused arg-max) + D2H every step ----
+    # Each sample's six input tensors live in ONE pinned staging buffer (what a collate function
+    # would produce), so a step is one H2D copy, the module call, and one D2H copy of the occupancy
+    # prediction.  The host consumes prediction i-1 while step i is in flight (two result buffers),
+    # i.e. copies and kernels of consecutive steps overlap CPU work but every step's copies are
+    # inside the timed region.
     module = LocalAggregator(**kw).to(dev)
-    module.validate = False     # the D2H read of the prediction below is the step's sync point
-    host = [{k: v.pin_memory() for k, v in (inp0 if i == 0 else make_splat_inputs(WORKLOAD, seed=rank * 100 + i, perturb=True)[1]).items()}
-            for i in range(2)]
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    pred_host = torch.empty(N, dtype=torch.uint8).pin_memory()
-    d2h = pred_host.numel()
+    module.validate = False     # the D2H read of the prediction is the step's synchronisation point
+    n_host = 3
+    layouts, host = [], []
+    for i in range(n_host):
+        inp = inp0 if i == 0 else make_splat_inputs(WORKLOAD, seed=rank * 100 + i, perturb=True)[1]
+        offs, off = {}, 0
+        for k, v in inp.items():
+            offs[k] = (off, v.numel(), tuple(v.shape))
+            off += (v.numel() + 63) // 64 * 64          # 256-byte aligned slices
+        buf = torch.empty(off, dtype=torch.float32).pin_memory()
+        for k, v in inp.items():
+            o, nel, _ = offs[k]
+            buf[o:o + nel].copy_(v.reshape(-1))
+        layouts.append(offs)
+        host.append(buf)
+    h2d = host[0].numel() * 4
+    pred_host = [torch.empty(N, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h = pred_host[0].numel()
+    consumed = [0]
 
     def e2e_step(i):
-        hin = host[i % 2]
-        d = {k: v.to(dev, non_blocking=True) for k, v in hin.items()}
+        dbuf = host[i % n_host].to(dev, non_blocking=True)
+        d = {k: dbuf[o:o + nel].view(shape) for k, (o, nel, shape) in layouts[i % n_host].items()}
         _logits, occ = module.forward_with_occupancy(d["pts"], d["means"], d["opa"], d["sem"], d["scales"], d["cov"])
-        pred_host.copy_(occ, non_blocking=True)
+        pred_host[i & 1].copy_(occ, non_blocking=True)
+        done[i & 1].record(stream)
         if world > 1:
-            dist.all_reduce(loss_buf)
-        stream.synchronize()        # the caller consumes the prediction on the host every step
+            pending.append(dist.all_reduce(loss_buf, async_op=True))
+        if i > 0:                                  # consume the previous step's prediction on the host
+            done[(i - 1) & 1].synchronize()
+            consumed[0] += int(pred_host[(i - 1) & 1][0])
 
-    for i in range(3):
+    for i in range(4):
         e2e_step(i)
-    e2e_steps = max(5, min(K, 50))
+    e2e_steps = max(5, min(K, 100))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -271,7 +293,9 @@ def main():
     e2e_ms = max(e2e_ms_dev, 0.0) / e2e_steps
     e2e = {"value": world * G_COUNTED / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall * 1e3 / e2e_steps,
-           "api": "local_aggregate.LocalAggregator.forward_with_occupancy (validate=False): logits + fused arg-max"}
+           "api": "local_aggregate.LocalAggregator.forward_with_occupancy (validate=False): one pinned staging "
+                  "buffer per sample -> H2D, logits + fused arg-max, D2H of the uint8 occupancy; host reads "
+                  "prediction i-1 while step i runs"}
 
     extras = {}
     if rank == 0 and not args.no_extras:

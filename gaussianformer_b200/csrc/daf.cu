@@ -83,7 +83,7 @@ template <> struct Vec<1> {
 // VEC = 4: C % 128 == 0 and (C/Gr)/4 a power of two <= 32 (a group is a run of whole lanes).
 // VEC = 1: any C, Gr.
 template <int VEC, bool BACKWARD>
-__global__ void __launch_bounds__(kDafThreads, 2) daf_kernel(const DafParams p) {
+__global__ void __launch_bounds__(kDafThreads) daf_kernel(const DafParams p) {
     using V = Vec<VEC>;
     using T = typename V::T;
     const int lane = threadIdx.x & 31;

@@ -179,8 +179,166 @@ __global__ void __launch_bounds__(kDafThreads) daf_kernel(const DafParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path (C % 128 == 0, a group = whole lanes, M*L <= 32): one warp per sampling point, and the
+// bilinear setup of each (camera, level) pair is computed by ONE lane instead of all 32 — the r01
+// profile showed the first-generation kernel to be instruction-bound (224 M warp instructions,
+// L2 at 27 %), almost all of it redundant warp-uniform setup arithmetic.
+//   lane p < M*L      : pair p = (camera p / L, level p % L): gate, 4 corner rows (clamped to a valid
+//                       row), 4 corner weights (zero for corners outside the map) -> per-warp smem
+//   ballot of the gate: only visible pairs are visited, in ascending (camera, level) order
+//   every visit       : 2-3 uniform LDS.128 for the setup, one weight load, 4 coalesced 16-byte row
+//                       loads per lane, 16 FMAs
+// ------------------------------------------------------------------------------------------------
+struct PairSetup {     // 64 bytes per (camera, level) pair
+    int row[4];        // element offset of each corner row inside the batch's feature block (row * C)
+    float w[4];        // bilinear corner weights, 0 where the corner is outside the map
+    float lh, lw;      // fractional parts (backward only)
+    float fh, fw;      // level height / width as floats (backward only)
+    int ok;            // bit k: corner k lies inside the map
+    int cam;           // camera of this pair
+    int pad0, pad1;
+};
+
+__device__ __forceinline__ bool pair_setup(const DafParams &p, const int *lh, const int *lw, const int *ls,
+                                           long long bp, int pair, PairSetup &o) {
+    const int L = p.d.num_scale, M = p.d.num_cams, F = p.d.num_feat, C = p.d.num_embeds;
+    const int m = pair / L, lv = pair - m * L;
+    const float lx = __ldg(p.loc + (bp * M + m) * 2), ly = __ldg(p.loc + (bp * M + m) * 2 + 1);
+    const bool gate = lx > 0.f && lx < 1.f && ly > 0.f && ly < 1.f;
+    const int h = lh[lv], w = lw[lv];
+    const float y_im = ly * static_cast<float>(h) - 0.5f, x_im = lx * static_cast<float>(w) - 0.5f;
+    const float yf = floorf(y_im), xf = floorf(x_im);
+    const int y0 = static_cast<int>(yf), x0 = static_cast<int>(xf);
+    o.lh = y_im - yf; o.lw = x_im - xf;
+    o.fh = static_cast<float>(h); o.fw = static_cast<float>(w);
+    const float hh = 1.f - o.lh, hw = 1.f - o.lw;
+    const bool oky0 = y0 >= 0, oky1 = y0 + 1 <= h - 1, okx0 = x0 >= 0, okx1 = x0 + 1 <= w - 1;
+    const int cy0 = max(y0, 0), cy1 = min(y0 + 1, h - 1), cx0 = max(x0, 0), cx1 = min(x0 + 1, w - 1);
+    const int base = m * F + ls[lv];
+    o.row[0] = (base + cy0 * w + cx0) * C;
+    o.row[1] = (base + cy0 * w + cx1) * C;
+    o.row[2] = (base + cy1 * w + cx0) * C;
+    o.row[3] = (base + cy1 * w + cx1) * C;
+    o.w[0] = (oky0 && okx0) ? hh * hw : 0.f;
+    o.w[1] = (oky0 && okx1) ? hh * o.lw : 0.f;
+    o.w[2] = (oky1 && okx0) ? o.lh * hw : 0.f;
+    o.w[3] = (oky1 && okx1) ? o.lh * o.lw : 0.f;
+    o.ok = (oky0 && okx0 ? 1 : 0) | (oky0 && okx1 ? 2 : 0) | (oky1 && okx0 ? 4 : 0) | (oky1 && okx1 ? 8 : 0);
+    o.cam = m;
+    o.pad0 = o.pad1 = 0;
+    return gate;
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kDafThreads) daf_fast_kernel(const DafParams p) {
+    __shared__ int lh[kMaxLevels], lw[kMaxLevels], ls[kMaxLevels];
+    __shared__ __align__(16) PairSetup s_pair[kDafThreads / 32][32];
+    if (threadIdx.x < p.d.num_scale) {
+        lh[threadIdx.x] = p.shape[2 * threadIdx.x];
+        lw[threadIdx.x] = p.shape[2 * threadIdx.x + 1];
+        ls[threadIdx.x] = p.start[threadIdx.x];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = p.d.num_embeds, M = p.d.num_cams, L = p.d.num_scale, Gr = p.d.num_groups, F = p.d.num_feat;
+    const int npair = M * L;
+    const int gdim = C / Gr;
+    const long long npts = static_cast<long long>(p.d.batch) * p.d.num_pts;
+    const long long warps = static_cast<long long>(gridDim.x) * (kDafThreads / 32);
+    PairSetup *mine = s_pair[warp];
+
+    for (long long bp = static_cast<long long>(blockIdx.x) * (kDafThreads / 32) + warp; bp < npts; bp += warps) {
+        const int b = static_cast<int>(bp / p.d.num_pts);
+        bool gate = false;
+        if (lane < npair) {
+            PairSetup ps;
+            gate = pair_setup(p, lh, lw, ls, bp, lane, ps);
+            mine[lane] = ps;
+        }
+        const uint32_t visible = __ballot_sync(0xffffffffu, gate);
+        __syncwarp();
+        const float *featb = p.feat + static_cast<long long>(b) * M * F * C;
+        const float *wpt = p.weights + bp * npair * Gr;
+        for (int c0 = lane * 4; c0 < C; c0 += 128) {
+            const int grp = c0 / gdim;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 gout = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (BACKWARD) gout = __ldg(reinterpret_cast<const float4 *>(p.grad_out + bp * C + c0));
+            float gx = 0.f, gy = 0.f;
+            uint32_t todo = visible;
+            while (todo) {
+                const int pr = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int4 rows = *reinterpret_cast<const int4 *>(mine[pr].row);      // warp-uniform loads
+                const float4 cw = *reinterpret_cast<const float4 *>(mine[pr].w);
+                const float wt = __ldg(wpt + pr * Gr + grp);
+                const float4 v0 = __ldg(reinterpret_cast<const float4 *>(featb + rows.x + c0));
+                const float4 v1 = __ldg(reinterpret_cast<const float4 *>(featb + rows.y + c0));
+                const float4 v2 = __ldg(reinterpret_cast<const float4 *>(featb + rows.z + c0));
+                const float4 v3 = __ldg(reinterpret_cast<const float4 *>(featb + rows.w + c0));
+                if (!BACKWARD) {
+                    const float a0 = cw.x * wt, a1 = cw.y * wt, a2 = cw.z * wt, a3 = cw.w * wt;
+                    acc.x = fmaf(a0, v0.x, acc.x); acc.y = fmaf(a0, v0.y, acc.y); acc.z = fmaf(a0, v0.z, acc.z); acc.w = fmaf(a0, v0.w, acc.w);
+                    acc.x = fmaf(a1, v1.x, acc.x); acc.y = fmaf(a1, v1.y, acc.y); acc.z = fmaf(a1, v1.z, acc.z); acc.w = fmaf(a1, v1.w, acc.w);
+                    acc.x = fmaf(a2, v2.x, acc.x); acc.y = fmaf(a2, v2.y, acc.y); acc.z = fmaf(a2, v2.z, acc.z); acc.w = fmaf(a2, v2.w, acc.w);
+                    acc.x = fmaf(a3, v3.x, acc.x); acc.y = fmaf(a3, v3.y, acc.y); acc.z = fmaf(a3, v3.z, acc.z); acc.w = fmaf(a3, v3.w, acc.w);
+                } else {
+                    const float4 fr = *reinterpret_cast<const float4 *>(&mine[pr].lh);
+                    const int2 okcam = *reinterpret_cast<const int2 *>(&mine[pr].ok);
+                    const float2 frac = make_float2(fr.x, fr.y), dims = make_float2(fr.z, fr.w);
+                    const int ok = okcam.x;
+                    // d(out)/d(feat corner) = corner weight * aggregation weight, for corners inside the map
+                    float *gfb = p.grad_feat + static_cast<long long>(b) * M * F * C + c0;
+                    if (ok & 1) atomicAdd(reinterpret_cast<float4 *>(gfb + rows.x), make_float4(cw.x * wt * gout.x, cw.x * wt * gout.y, cw.x * wt * gout.z, cw.x * wt * gout.w));
+                    if (ok & 2) atomicAdd(reinterpret_cast<float4 *>(gfb + rows.y), make_float4(cw.y * wt * gout.x, cw.y * wt * gout.y, cw.y * wt * gout.z, cw.y * wt * gout.w));
+                    if (ok & 4) atomicAdd(reinterpret_cast<float4 *>(gfb + rows.z), make_float4(cw.z * wt * gout.x, cw.z * wt * gout.y, cw.z * wt * gout.z, cw.z * wt * gout.w));
+                    if (ok & 8) atomicAdd(reinterpret_cast<float4 *>(gfb + rows.w), make_float4(cw.w * wt * gout.x, cw.w * wt * gout.y, cw.w * wt * gout.z, cw.w * wt * gout.w));
+                    // g . v_k for the four corners (outside corners carry weight 0; their clamped values are masked below)
+                    const float m0 = (ok & 1) ? 1.f : 0.f, m1 = (ok & 2) ? 1.f : 0.f, m2 = (ok & 4) ? 1.f : 0.f, m3 = (ok & 8) ? 1.f : 0.f;
+                    const float d0 = m0 * (gout.x * v0.x + gout.y * v0.y + gout.z * v0.z + gout.w * v0.w);
+                    const float d1 = m1 * (gout.x * v1.x + gout.y * v1.y + gout.z * v1.z + gout.w * v1.w);
+                    const float d2 = m2 * (gout.x * v2.x + gout.y * v2.y + gout.z * v2.z + gout.w * v2.w);
+                    const float d3 = m3 * (gout.x * v3.x + gout.y * v3.y + gout.z * v3.z + gout.w * v3.w);
+                    const float lhh = frac.x, lww = frac.y, hh = 1.f - lhh, hw = 1.f - lww;
+                    // d(out)/d(weight) = sampled value . g   (cuda.cu:117-119)
+                    float gw = hh * hw * d0 + hh * lww * d1 + lhh * hw * d2 + lhh * lww * d3;
+                    // d(val)/d(x_im), d(val)/d(y_im)   (cuda.cu:85-121)
+                    gx = fmaf(dims.y * wt, -hh * d0 + hh * d1 - lhh * d2 + lhh * d3, gx);
+                    gy = fmaf(dims.x * wt, -hw * d0 - lww * d1 + hw * d2 + lww * d3, gy);
+                    const int lanes_per_group = gdim / 4;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1)
+                        if (o < lanes_per_group) gw += __shfl_xor_sync(0xffffffffu, gw, o);
+                    if ((lane & (lanes_per_group - 1)) == 0) p.grad_weights[(bp * npair + pr) * Gr + grp] += gw;
+                    // the location gradient of a camera is complete after its last visible level
+                    const int m = okcam.y;
+                    const bool cam_done = todo == 0 || mine[__ffs(todo) - 1].cam != m;
+                    if (cam_done) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            gx += __shfl_xor_sync(0xffffffffu, gx, o);
+                            gy += __shfl_xor_sync(0xffffffffu, gy, o);
+                        }
+                        if (lane == 0) {
+                            float *gl = p.grad_loc + (bp * M + m) * 2;
+                            gl[0] += gx;
+                            gl[1] += gy;
+                        }
+                        gx = 0.f; gy = 0.f;
+                    }
+                }
+            }
+            if (!BACKWARD) *reinterpret_cast<float4 *>(p.out + bp * C + c0) = acc;
+        }
+        __syncwarp();   // the next point overwrites this warp's setup slots
+    }
+}
+
 static bool vec4_ok(const gf_daf_desc &d) {
     if (d.num_embeds % 128 != 0) return false;
+    if (d.num_cams * d.num_scale > 32) return false;
+    if (static_cast<long long>(d.num_cams) * d.num_feat * d.num_embeds >= (1ll << 31)) return false;  // int32 row offsets
     const int gdim = d.num_embeds / d.num_groups;
     if (gdim % 4 != 0) return false;
     const int lpg = gdim / 4;
@@ -196,10 +354,10 @@ int launch_daf(const gf_daf_desc &d, const DafParams &dp, bool backward, int num
     const int grid = static_cast<int>(want < cap ? want : cap);
     const bool v4 = vec4_ok(d);
     if (backward) {
-        if (v4) daf_kernel<4, true><<<grid, kDafThreads, 0, stream>>>(dp);
+        if (v4) daf_fast_kernel<true><<<grid, kDafThreads, 0, stream>>>(dp);
         else daf_kernel<1, true><<<grid, kDafThreads, 0, stream>>>(dp);
     } else {
-        if (v4) daf_kernel<4, false><<<grid, kDafThreads, 0, stream>>>(dp);
+        if (v4) daf_fast_kernel<false><<<grid, kDafThreads, 0, stream>>>(dp);
         else daf_kernel<1, false><<<grid, kDafThreads, 0, stream>>>(dp);
     }
     GF_CUDA_TRY(cudaGetLastError());

@@ -373,6 +373,25 @@ def side_measurements(dev, kw, inp0, resident, desc):
         out["extras_error"] = repr(e)
     try:
         from oracle import build_ref
+        if build_ref.available("gf_ref_daf"):
+            mod = build_ref.load_ref("gf_ref_daf")
+            fms, loc, w = make_daf_inputs(seed=0)
+            feat, shape, start = DAF.feature_maps_format([f.to(dev) for f in fms])
+            feat = feat.contiguous()
+            loc, w, shape_i, start_i = loc.to(dev), w.to(dev), shape.int(), start.int()
+            ref_f = timeit(lambda: mod.deformable_aggregation_forward(feat, shape_i, start_i, loc, w), reps=10)
+            g = torch.randn(1, loc.shape[1], 128, device=dev)
+            gf, gl, gw = torch.zeros_like(feat), torch.zeros_like(loc), torch.zeros_like(w)
+            ref_b = timeit(lambda: mod.deformable_aggregation_backward(feat, shape_i, start_i, loc, w, g, gf, gl, gw), reps=5)
+            feat.requires_grad_(True); loc.requires_grad_(True); w.requires_grad_(True)
+            o = DAF.apply(feat, shape, start, loc, w)
+            out["daf_bwd_ms"] = timeit(lambda: torch.autograd.grad(o, [feat, loc, w], g, retain_graph=True), reps=5)
+            out["ref_daf_op"] = {"fwd_ms": ref_f, "bwd_kernel_ms": ref_b, "what": "reference deformable_aggregation op "
+                                 "compiled for sm_100a, same GPU, same inputs (backward without its three zero fills)"}
+    except Exception as e:
+        out["ref_daf_op"] = {"error": repr(e)}
+    try:
+        from oracle import build_ref
         if build_ref.available("gf_ref_localagg"):
             mod = build_ref.load_ref("gf_ref_localagg")
             t = {k: v[0].to(dev) for k, v in inp0.items()}

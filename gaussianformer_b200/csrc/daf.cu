@@ -231,7 +231,7 @@ __device__ __forceinline__ bool pair_setup(const DafParams &p, const int *lh, co
 }
 
 template <bool BACKWARD>
-__global__ void __launch_bounds__(kDafThreads) daf_fast_kernel(const DafParams p) {
+__global__ void __launch_bounds__(kDafThreads, BACKWARD ? 3 : 4) daf_fast_kernel(const DafParams p) {
     __shared__ int lh[kMaxLevels], lw[kMaxLevels], ls[kMaxLevels];
     __shared__ __align__(16) PairSetup s_pair[kDafThreads / 32][32];
     if (threadIdx.x < p.d.num_scale) {

@@ -201,9 +201,8 @@ struct PairSetup {     // 64 bytes per (camera, level) pair
 };
 
 __device__ __forceinline__ bool pair_setup(const DafParams &p, const int *lh, const int *lw, const int *ls,
-                                           long long bp, int pair, PairSetup &o) {
-    const int L = p.d.num_scale, M = p.d.num_cams, F = p.d.num_feat, C = p.d.num_embeds;
-    const int m = pair / L, lv = pair - m * L;
+                                           long long bp, int m, int lv, PairSetup &o) {
+    const int M = p.d.num_cams, F = p.d.num_feat, C = p.d.num_embeds;
     const float lx = __ldg(p.loc + (bp * M + m) * 2), ly = __ldg(p.loc + (bp * M + m) * 2 + 1);
     const bool gate = lx > 0.f && lx < 1.f && ly > 0.f && ly < 1.f;
     const int h = lh[lv], w = lw[lv];
@@ -247,13 +246,15 @@ __global__ void __launch_bounds__(kDafThreads, BACKWARD ? 3 : 4) daf_fast_kernel
     const long long npts = static_cast<long long>(p.d.batch) * p.d.num_pts;
     const long long warps = static_cast<long long>(gridDim.x) * (kDafThreads / 32);
     PairSetup *mine = s_pair[warp];
+    const int my_cam = lane / L, my_lv = lane - my_cam * L;   // lane <-> (camera, level) pair, fixed for the kernel
+    const bool small_index = npts < (1ll << 31);
 
     for (long long bp = static_cast<long long>(blockIdx.x) * (kDafThreads / 32) + warp; bp < npts; bp += warps) {
-        const int b = static_cast<int>(bp / p.d.num_pts);
+        const int b = small_index ? static_cast<int>(bp) / p.d.num_pts : static_cast<int>(bp / p.d.num_pts);
         bool gate = false;
         if (lane < npair) {
             PairSetup ps;
-            gate = pair_setup(p, lh, lw, ls, bp, lane, ps);
+            gate = pair_setup(p, lh, lw, ls, bp, my_cam, my_lv, ps);
             mine[lane] = ps;
         }
         const uint32_t visible = __ballot_sync(0xffffffffu, gate);

@@ -189,3 +189,35 @@ def test_fused_argmax_matches_logits():
     lg2, occ2 = m.forward_with_occupancy(t["pts"][:, perm].contiguous(), t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
     first2 = (lg2 == lg2.max(dim=1, keepdim=True).values).float().argmax(dim=1)
     assert torch.equal(occ2.long(), first2)
+
+
+@pytest.mark.parametrize("C", [16, 17, 19, 20])
+@pytest.mark.parametrize("variant", ["base", "prob"])
+def test_other_class_counts(C, variant):
+    """The reference hard-codes 18 classes (src/config.h:15); the library is compiled for 16..20."""
+    cfg = "tiny" if variant == "base" else "tiny_prob"
+    kw, inp, _ = h.splat_case(cfg, 9, True)
+    G = inp["sem"].shape[1]
+    sem = torch.rand(1, G, C, generator=torch.Generator().manual_seed(C))
+    inp = dict(inp, sem=sem)
+    m = h.make_module(kw, variant)
+    t = h.to_dev(inp, requires_grad=True)
+    out = m(t["pts"], t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
+    ref = h.oracle_forward(kw, inp, variant)
+    first = out if variant == "base" else out[0]
+    stable = np.ones(first.shape[0], bool) if variant == "base" else np.abs(ref["probability"] - 1e-9) > 1e-10
+    h.assert_close(first.detach().cpu().numpy()[stable], ref["logits"][stable], what=f"C={C} logits")
+    gen = torch.Generator().manual_seed(1)
+    if variant == "base":
+        g = (torch.randn(first.shape, generator=gen),)
+        first.backward(g[0].cuda())
+        saved = None
+    else:
+        g = (torch.randn(out[0].shape, generator=gen), torch.randn(out[1].shape, generator=gen),
+             torch.randn(out[2].shape, generator=gen))
+        torch.autograd.backward(list(out), [x.cuda() for x in g])
+        saved = dict(logits=out[0].detach().cpu().numpy(), bin_logits=out[1].detach().cpu().numpy(),
+                     probability=h.oracle_forward(kw, inp, variant, "f32")["probability"])
+    gm, go, gs, gc = h.oracle_backward(kw, inp, variant, tuple(x.numpy() for x in g), saved)
+    h.assert_close(t["sem"].grad[0].cpu().numpy(), gs, rtol=2e-3, atol=5 * h.grad_tolerance(gs), what=f"C={C} grad sem")
+    h.assert_close(t["means"].grad[0].cpu().numpy(), gm, rtol=2e-3, atol=5 * h.grad_tolerance(gm), what=f"C={C} grad means")

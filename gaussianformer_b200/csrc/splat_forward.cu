@@ -14,6 +14,9 @@ namespace gf {
 
 extern thread_local cudaEvent_t g_ev_before, g_ev_after;  // measurement hooks (cabi.cu)
 
+#ifndef GF_RENDER_CTAS
+#define GF_RENDER_CTAS 4   // resident CTAs per SM the base tile kernel is compiled for
+#endif
 #ifndef GF_RENDER_VOX
 #define GF_RENDER_VOX 4   // voxels per thread of the tile kernel (2 or 4)
 #endif
@@ -54,7 +57,7 @@ __device__ __forceinline__ void mbar_arrive_one(uint64_t *bar) {
 //     touch its footprint (ballot -> bit loop), a lane tests its column with one AND and its four
 //     voxels with one shift, and the class accumulation runs on packed fp32 pairs (FFMA2).
 template <int C, bool PROB, int VOX>
-__global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : 4) : (PROB ? 2 : 3)) render_tile_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CTAS) : (PROB ? 2 : 3)) render_tile_kernel(const RenderParams p) {
     constexpr int NT = 512 / VOX, NWARP = NT / 32;
     constexpr uint32_t VMASK = (1u << VOX) - 1u;
     constexpr int REC = rec_floats(C);
@@ -406,6 +409,7 @@ static bool use_simt_render() {
     return cached == 1;
 }
 
+#ifdef GF_ENABLE_VOX2
 // voxels per thread of the tile kernel: GF_B200_VOX=2|4 overrides the default
 static int render_vox() {
     static int cached = 0;
@@ -415,6 +419,7 @@ static int render_vox() {
     }
     return cached;
 }
+#endif
 
 template <int C, bool PROB>
 static int launch_render_t(const RenderParams &rp, bool tile_path, int num_sms, cudaStream_t stream) {
@@ -424,9 +429,11 @@ static int launch_render_t(const RenderParams &rp, bool tile_path, int num_sms, 
         GF_REQUIRE(rp.nby <= 65535 && nbx <= 65535, GF_ERR_UNSUPPORTED, "splat: grid too large for the render launch");
         const dim3 grid(rp.nzc, rp.nby, nbx);
         if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_before, stream));
+#ifdef GF_ENABLE_VOX2   // experiment kept in the source: 2 voxels per thread (measured equal to 4 on B200)
         if (render_vox() == 2)
             render_tile_kernel<C, PROB, 2><<<grid, 256, sizeof(RenderSmem<C, 2>), stream>>>(rp);
         else
+#endif
             render_tile_kernel<C, PROB, 4><<<grid, 128, sizeof(RenderSmem<C, 4>), stream>>>(rp);
         GF_CUDA_TRY(cudaGetLastError());
         if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_after, stream));

@@ -40,7 +40,7 @@ constexpr uint32_t kTmemCols = 32;
 //   A  (K-major,  SWIZZLE_NONE): (m%8)*16 + (m/8)*SBO_A + (k/4)*LBO_A + (k%4)*4,  SBO_A = 128, LBO_A = 2048
 //   B  (K-major,  SWIZZLE_NONE): (n%8)*16 + (n/8)*SBO_B + (k/4)*LBO_B + (k%4)*4,  SBO_B = 128, LBO_B = 512
 // (LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = distance between 8-row
-// groups; verified on hardware by scratch/umma_test.cu.  MN-major operands are NOT usable with
+// groups; verified on hardware by tools/umma_test.cu.  MN-major operands are NOT usable with
 // kind::tf32 + SWIZZLE_NONE: the same probe returns all zeros for them.)
 constexpr uint32_t kSboA = 128, kLboA = 2048, kSboB = 128, kLboB = (kTcN / 8) * 128;
 

@@ -108,7 +108,7 @@ def run_reference_arm(args):
         return
     import oracle
     from gaussianformer_b200.synthetic import make_splat_inputs
-    kw, inp, _ = make_splat_inputs(WORKLOAD, seed=0, perturb=True)
+    kw, inp, _ = make_splat_inputs(WORKLOAD, seed=0, perturb=False)
     for _ in range(max(1, min(args.warmup, 2))):
         _cpu_port_once(kw, inp)
     steps = max(1, min(args.steps, 10))
@@ -133,6 +133,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (bwd, prob, DAF, ref op)")
+    ap.add_argument("--perturb", action="store_true", help="jitter every point inside its voxel (LoadOccupancySurroundOcc(perturb=True)); "
+                    "the shipped configs and BASELINE.md use exact voxel centres")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -158,10 +160,11 @@ def main():
     K = args.steps
 
     # ---- resident inputs: N_SETS different samples (seeded), rotated so no step re-reads L2 -------
-    kw, inp0, _ = make_splat_inputs(WORKLOAD, seed=rank * 100, perturb=True)
+    PERTURB = args.perturb
+    kw, inp0, _ = make_splat_inputs(WORKLOAD, seed=rank * 100, perturb=PERTURB)
     sets = []
     for i in range(N_SETS):
-        _, inp, _ = (kw, inp0, None) if i == 0 else make_splat_inputs(WORKLOAD, seed=rank * 100 + i, perturb=True)
+        _, inp, _ = (kw, inp0, None) if i == 0 else make_splat_inputs(WORKLOAD, seed=rank * 100 + i, perturb=PERTURB)
         t = {k: v[0].to(dev).contiguous() for k, v in inp.items()}
         t["cov"] = t["cov"].reshape(-1, 9).contiguous()
         sets.append(t)
@@ -252,7 +255,7 @@ def main():
     n_host = 3
     layouts, host = [], []
     for i in range(n_host):
-        inp = inp0 if i == 0 else make_splat_inputs(WORKLOAD, seed=rank * 100 + i, perturb=True)[1]
+        inp = inp0 if i == 0 else make_splat_inputs(WORKLOAD, seed=rank * 100 + i, perturb=PERTURB)[1]
         offs, off = {}, 0
         for k, v in inp.items():
             offs[k] = (off, v.numel(), tuple(v.shape))
@@ -323,7 +326,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{WORKLOAD}: 25600 Gaussians (+1 empty) -> 200x200x16x18 voxels, "
-                                       f"batch 1 per GPU, perturbed voxel-centre points",
+                                       f"batch 1 per GPU, points = " + ("perturbed voxel centres" if PERTURB else "voxel centres (BASELINE.md §3)"),
                            "l2": f"{N_SETS} rotating input/output/workspace sets "
                                  f"({N_SETS * (alg + ws_bytes) / 1e6:.0f} MB) > 126 MB L2",
                            "parallelism": f"dp{world} (one sample per GPU, scalar loss all-reduce)"},

@@ -134,6 +134,10 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
             }
         if (stray) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
     }
+    // do my VOX points share x and y exactly?  (decided once; the branch on it is warp-uniform in practice)
+    bool column = true;
+#pragma unroll
+    for (int v = 1; v < VOX; ++v) column = column && px[v] == px[0] && py[v] == py[0];
     // entry word: x mask [0,8) | y mask [8,12) | z mask [16,32)
     const uint32_t my_xy = (1u << lx) | (1u << (8 + ly));
     const int my_zshift = 16 + VOX * lq;
@@ -261,7 +265,26 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
                     const float4 g0 = r4[0], g1 = r4[1];
                     const float2 g2 = *reinterpret_cast<const float2 *>(r4 + 2);
                     float wv[VOX];
-                    // quadratic form on packed fp32 pairs: voxels (0,1) and (2,3) share each instruction
+                    if (column) {
+                        // My VOX points share x and y (voxel centres of one z column — every shipped config,
+                        // dataset/transform_3d.py:484-499 without perturbation): the exponent is a quadratic
+                        // in dz alone, q = (cc*dz + B)*dz + A, with A and B evaluated once per record.
+                        const float dx = g0.x - px[0], dy = g0.y - py[0];
+                        float t1 = g1.x * dx;
+                        t1 = fmaf(g1.w, dy, t1);
+                        float A = t1 * dx;
+                        A = fmaf(g1.y * dy, dy, A);
+                        const float B = fmaf(g2.x, dy, g2.y * dx);
+#pragma unroll
+                        for (int v = 0; v < VOX; ++v) {
+                            const float dz = g0.z - pz[v];
+                            const float q = fmaf(fmaf(g1.z, dz, B), dz, A);
+                            const float E = ((zb >> v) & 1u) ? ex2_approx(q) : 0.f;
+                            wv[v] = g0.w * E;
+                            if (PROB) { zsum[v] += wv[v]; dens[v] += E; keep[v] *= (1.f - E); }
+                        }
+                    } else {
+                    // general points: quadratic form on packed fp32 pairs, voxels (0,1) and (2,3) share each instruction
 #pragma unroll
                     for (int h2 = 0; h2 < VOX / 2; ++h2) {
                         const int v0 = 2 * h2, v1 = v0 + 1;
@@ -284,6 +307,7 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
                             zsum[v0] += wv[v0]; dens[v0] += E0; keep[v0] *= (1.f - E0);
                             zsum[v1] += wv[v1]; dens[v1] += E1; keep[v1] *= (1.f - E1);
                         }
+                    }
                     }
 #pragma unroll
                     for (int c4 = 0; c4 < (C + 3) / 4; ++c4) {

@@ -80,6 +80,24 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def _bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to the GPU, so that the pinned host
+    buffers of the e2e leg are first-touched on the GPU's NUMA node (a remote node can cut the H2D
+    rate several-fold).  Best effort: returns a short description or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {index}"
+    except Exception:
+        pass
+    return None
+
+
 def _measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -151,6 +169,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback of the product path)"
     torch.cuda.set_device(local_rank)
+    numa = _bind_to_gpu_numa_node(local_rank)   # pinned staging buffers must live next to the GPU
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -304,6 +323,7 @@ def main():
     e2e_ms = max(e2e_ms_dev, 0.0) / e2e_steps
     e2e = {"value": world * G_COUNTED / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall * 1e3 / e2e_steps,
+           "host_numa_binding": numa,
            "api": "local_aggregate.LocalAggregator.forward_with_occupancy (validate=False): one pinned staging "
                   "buffer per sample -> H2D on a copy stream, logits + fused arg-max, D2H of the uint8 occupancy; "
                   "host reads prediction i-1 while step i runs"}

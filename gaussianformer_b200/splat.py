@@ -35,7 +35,24 @@ def _ptr(t):
 
 
 def _f32c(t):
-    return t.detach().contiguous().float()
+    t = t.detach()
+    if t.dtype is torch.float32 and t.is_contiguous():
+        return t                      # the common case costs two attribute reads
+    return t.contiguous().float()
+
+
+_DESC_CACHE = {}
+_WS_BYTES = {}   # id(cached desc) -> forward workspace bytes
+
+
+def _cached_desc(key, *args):
+    """ctypes descriptors are immutable after construction here; build each distinct one once."""
+    d = _DESC_CACHE.get(key)
+    if d is None:
+        d = _make_desc(*args)
+        if len(_DESC_CACHE) < 256:
+            _DESC_CACHE[key] = d
+    return d
 
 
 def _make_desc(G, N, C, H, W, D, variant, radii_axes, cov_stride, pc_min, grid_size, scale_multiplier, radii_min):
@@ -69,9 +86,13 @@ def splat_forward_raw(desc, pts, means, opa, sem, cov, *, points_int=None, means
             binl, dens, probability = aux[0], aux[1], aux[2]
         else:
             binl = dens = probability = None
-        ws_bytes = L.gf_splat_forward_workspace_bytes(ctypes.byref(desc))
-        if ws_bytes == 0:
-            raise _lib.GfError(L.gf_last_error().decode())
+        ws_bytes = _WS_BYTES.get(id(desc))
+        if ws_bytes is None:
+            ws_bytes = L.gf_splat_forward_workspace_bytes(ctypes.byref(desc))
+            if ws_bytes == 0:
+                raise _lib.GfError(L.gf_last_error().decode())
+            if id(desc) in map(id, _DESC_CACHE.values()):
+                _WS_BYTES[id(desc)] = ws_bytes
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         ins = SplatInputs(_ptr(pts), _ptr(points_int), _ptr(means), _ptr(means_int), _ptr(opa), _ptr(sem), _ptr(cov),
                           _ptr(radii), _ptr(scales))
@@ -131,9 +152,9 @@ class _SplatFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pts, means, opa, sem, scales, cov, cfg):
-        desc = _make_desc(means.shape[0], pts.shape[0], sem.shape[1], cfg["H"], cfg["W"], cfg["D"], cfg["variant"],
-                          cfg["radii_axes"], 9, cfg["pc_min"], cfg["grid_size"], cfg["scale_multiplier"],
-                          cfg["radii_min"])
+        args = (means.shape[0], pts.shape[0], sem.shape[1], cfg["H"], cfg["W"], cfg["D"], cfg["variant"],
+                cfg["radii_axes"], 9, cfg["pc_min"], cfg["grid_size"], cfg["scale_multiplier"], cfg["radii_min"])
+        desc = _cached_desc(args, *args)
         pts_c, means_c, opa_c, sem_c, scales_c = map(_f32c, (pts, means, opa, sem, scales))
         cov_c = _f32c(cov).reshape(-1, 9)
         (logits, binl, dens, probability), ws = splat_forward_raw(desc, pts_c, means_c, opa_c, sem_c, cov_c,
@@ -190,10 +211,14 @@ class _LocalAggregatorBase(nn.Module):
         _lib.lib()  # fail loudly at construction time if the extension is missing
 
     def _cfg(self):
-        return dict(H=self.H, W=self.W, D=self.D, variant=self._variant, radii_axes=self._radii_axes,
-                    pc_min=self._pc_min_host, grid_size=float(self.grid_size),
-                    scale_multiplier=float(self.scale_multiplier),
-                    radii_min=int(self.radii_min) if self.radii_min is not None else 0, validate=self.validate)
+        cfg = self.__dict__.get("_cfg_cache")
+        if cfg is None or cfg["validate"] != self.validate:
+            cfg = dict(H=self.H, W=self.W, D=self.D, variant=self._variant, radii_axes=self._radii_axes,
+                       pc_min=self._pc_min_host, grid_size=float(self.grid_size),
+                       scale_multiplier=float(self.scale_multiplier),
+                       radii_min=int(self.radii_min) if self.radii_min is not None else 0, validate=self.validate)
+            self.__dict__["_cfg_cache"] = cfg
+        return cfg
 
     def _run(self, pts, means3D, opacities, semantics, scales, cov3D):
         _require_cuda(pts, means3D, opacities, semantics, scales, cov3D)
@@ -229,9 +254,9 @@ class LocalAggregator(_LocalAggregatorBase):
         _require_cuda(pts, means3D, opacities, semantics, scales, cov3D)
         assert pts.shape[0] == 1
         cfg = self._cfg()
-        desc = _make_desc(means3D.shape[1], pts.shape[1], semantics.shape[2], cfg["H"], cfg["W"], cfg["D"],
-                          cfg["variant"], cfg["radii_axes"], 9, cfg["pc_min"], cfg["grid_size"],
-                          cfg["scale_multiplier"], cfg["radii_min"])
+        args = (means3D.shape[1], pts.shape[1], semantics.shape[2], cfg["H"], cfg["W"], cfg["D"], cfg["variant"],
+                cfg["radii_axes"], 9, cfg["pc_min"], cfg["grid_size"], cfg["scale_multiplier"], cfg["radii_min"])
+        desc = _cached_desc(args, *args)
         occ = torch.empty(pts.shape[1], dtype=torch.uint8, device=pts.device)
         (logits, _, _, _), ws = splat_forward_raw(desc, _f32c(pts[0]), _f32c(means3D[0]), _f32c(opacities[0]),
                                                  _f32c(semantics[0]), _f32c(cov3D[0]).reshape(-1, 9),

@@ -99,11 +99,27 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
             const int npass = min(kMaskPass, nsuper - base);
             for (int i = lane; i < npass; i += 32) s_mask[warp][i] = 0u;
             __syncwarp();
-            for (int sx = sx0; sx <= sx1; ++sx)
-                for (int sy = sy0; sy <= sy1; ++sy) {
-                    const int s = sx * p.nsy + sy - base;
-                    if (s >= 0 && s < npass) atomicOr(&s_mask[warp][s], 1u << lane);
+            // a lane sets its own bits when its box touches few supertiles; a box that touches many (the
+            // whole-grid "empty" Gaussian touches all of them) is spread over the 32 lanes instead
+            const int ny = sy1 - sy0 + 1, cnt = empty ? 0 : (sx1 - sx0 + 1) * ny;
+            const bool wide = cnt > 16;
+            if (!wide)
+                for (int sx = sx0; sx <= sx1; ++sx)
+                    for (int sy = sy0; sy <= sy1; ++sy) {
+                        const int s = sx * p.nsy + sy - base;
+                        if (s >= 0 && s < npass) atomicOr(&s_mask[warp][s], 1u << lane);
+                    }
+            uint32_t wides = __ballot_sync(0xffffffffu, wide);
+            while (wides) {
+                const int src = __ffs(wides) - 1;
+                wides &= wides - 1;
+                const int wx0 = __shfl_sync(0xffffffffu, sx0, src), wy0 = __shfl_sync(0xffffffffu, sy0, src);
+                const int wny = __shfl_sync(0xffffffffu, ny, src), wcnt = __shfl_sync(0xffffffffu, cnt, src);
+                for (int i = lane; i < wcnt; i += 32) {
+                    const int s = (wx0 + i / wny) * p.nsy + (wy0 + i % wny) - base;
+                    if (s >= 0 && s < npass) atomicOr(&s_mask[warp][s], 1u << src);
                 }
+            }
             __syncwarp();
             for (int i = lane; i < npass; i += 32)
                 p.masks[static_cast<size_t>(base + i) * p.nwords + word] = s_mask[warp][i];

@@ -146,42 +146,53 @@ struct ListParams {
     uint32_t initial_flags;
 };
 
-constexpr int kListThreads = 1024;
+constexpr int kListThreads = 256;
+constexpr int kListWordsPerThread = 4;   // consecutive mask words per thread and pass (keeps ascending order)
 
 __global__ void __launch_bounds__(kListThreads) list_kernel(const ListParams p) {
     const int s = blockIdx.x;
     const uint32_t *words = p.masks + static_cast<size_t>(s) * p.nwords;
     int32_t *list = p.lists + static_cast<size_t>(s) * p.G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ int s_warp[kListThreads / 32];
-    __shared__ int s_base;
-    if (threadIdx.x == 0) s_base = 0;
-    __syncthreads();
-    for (int w0 = 0; w0 < p.nwords; w0 += kListThreads) {
-        const int wi = w0 + threadIdx.x;
-        uint32_t bits = wi < p.nwords ? words[wi] : 0u;
-        const int cnt = __popc(bits);
+    __shared__ int s_warp[2][kListThreads / 32];
+    int base = 0, pass = 0;
+    for (int w0 = 0; w0 < p.nwords; w0 += kListThreads * kListWordsPerThread, ++pass) {
+        const int first = w0 + threadIdx.x * kListWordsPerThread;
+        uint32_t bits[kListWordsPerThread];
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < kListWordsPerThread; ++i) {
+            bits[i] = first + i < p.nwords ? __ldg(words + first + i) : 0u;
+            cnt += __popc(bits[i]);
+        }
         int incl = cnt;  // inclusive warp scan
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) s_warp[warp] = incl;
+        if (lane == 31) s_warp[pass & 1][warp] = incl;
         __syncthreads();
-        int warp_off = 0;
-        for (int k = 0; k < warp; ++k) warp_off += s_warp[k];
-        int pos = s_base + warp_off + incl - cnt;
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            list[pos++] = wi * 32 + b;
+        int warp_off = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < kListThreads / 32; ++k) {
+            const int c = s_warp[pass & 1][k];
+            if (k < warp) warp_off += c;
+            total += c;
         }
-        __syncthreads();
-        if (threadIdx.x == kListThreads - 1) s_base = pos;  // last thread holds the running total
-        __syncthreads();
+        int pos = base + warp_off + incl - cnt;
+#pragma unroll
+        for (int i = 0; i < kListWordsPerThread; ++i) {
+            uint32_t b = bits[i];
+            while (b) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                list[pos++] = (first + i) * 32 + bit;
+            }
+        }
+        base += total;
     }
-    if (threadIdx.x == 0) p.counts[s] = s_base;
+    if (threadIdx.x == 0) p.counts[s] = base;
 
     if (s == 0) {  // fold the pack kernel's error bits into the status word (also initialises it)
         uint32_t e = 0;

@@ -26,6 +26,7 @@ struct BwdParams {
     int32_t *v2p;      // [H*W*D]
     int32_t *big_list; // [G]
     int32_t *big_count;
+    int32_t *canon;    // non-zero after voxel_map_kernel iff N == H*W*D and point n sits in voxel n for all n
     float4 *aux;       // [N] prob only: per-point terms that do not depend on the Gaussian
 };
 
@@ -41,8 +42,10 @@ __global__ void __launch_bounds__(256) voxel_map_kernel(const BwdParams p) {
             iy = voxel_coord(p.in.pts[3 * n + 1], p.d.pc_min[1], p.d.grid_size);
             iz = voxel_coord(p.in.pts[3 * n + 2], p.d.pc_min[2], p.d.grid_size);
         }
-        if (ix < 0 || ix >= H || iy < 0 || iy >= W || iz < 0 || iz >= D) continue;
-        atomicMax(p.v2p + (static_cast<long long>(ix) * W + iy) * D + iz, static_cast<int>(n));
+        if (ix < 0 || ix >= H || iy < 0 || iy >= W || iz < 0 || iz >= D) { *p.canon = 0; continue; }
+        const long long v = (static_cast<long long>(ix) * W + iy) * D + iz;
+        if (v != n) *p.canon = 0;   // benign race: every writer stores 0 (the memset left it non-zero)
+        atomicMax(p.v2p + v, static_cast<int>(n));
     }
 }
 
@@ -276,9 +279,11 @@ __global__ void __launch_bounds__(kBwdThreads) backward_small_kernel(const BwdPa
     BoxWalk box;
     box.init(lo, hi, empty);
     const bool big = box.vol > kBigBox;
+    const bool canon = *p.canon != 0;   // then voxel index == point index and the map need not be read
     if (!big) {
         for (int i = lane; i < static_cast<int>(box.vol); i += 32) {
-            const int n = __ldg(p.v2p + box.voxel(i, p.d.W, p.d.D));
+            const long long v = box.voxel(i, p.d.W, p.d.D);
+            const long long n = canon ? v : __ldg(p.v2p + v);
             if (n >= 0) acc.visit(p, n);
         }
 #pragma unroll
@@ -316,8 +321,10 @@ __global__ void __launch_bounds__(kBwdThreads) backward_big_kernel(const BwdPara
         BoxWalk box;
         box.init(lo, hi, empty);
         const long long beg = box.vol * part / T, end = box.vol * (part + 1) / T;
+        const bool canon = *p.canon != 0;
         for (long long i = beg + threadIdx.x; i < end; i += kBwdThreads) {
-            const int n = __ldg(p.v2p + box.voxel(i, p.d.W, p.d.D));
+            const long long v = box.voxel(i, p.d.W, p.d.D);
+            const long long n = canon ? v : __ldg(p.v2p + v);
             if (n >= 0) acc.visit(p, n);
         }
 #pragma unroll
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(kBwdThreads) backward_big_kernel(const BwdPara
 // host side
 // ------------------------------------------------------------------------------------------------
 struct BwdWorkspace {
-    int32_t *v2p, *big_list, *big_count;
+    int32_t *v2p, *big_list, *big_count, *canon;
     float4 *aux;
     size_t bytes;
 };
@@ -362,6 +369,7 @@ void plan_backward_workspace(const gf_splat_desc &d, void *base, BwdWorkspace *w
         return p;
     };
     ws->big_count = reinterpret_cast<int32_t *>(take(64));
+    ws->canon = reinterpret_cast<int32_t *>(take(256));   // directly in front of v2p: one memset covers both
     ws->v2p = reinterpret_cast<int32_t *>(take(size_t(d.H) * d.W * d.D * 4));
     ws->big_list = reinterpret_cast<int32_t *>(take(size_t(d.G) * 4));
     ws->aux = reinterpret_cast<float4 *>(take(d.variant == GF_SPLAT_PROB ? size_t(d.N) * 16 : 0));
@@ -377,7 +385,10 @@ size_t backward_workspace_bytes(const gf_splat_desc &d) {
 template <int C, bool PROB>
 static int launch_backward_t(const BwdParams &bp, int num_sms, cudaStream_t stream) {
     const gf_splat_desc &d = bp.d;
-    GF_CUDA_TRY(cudaMemsetAsync(bp.v2p, 0xFF, size_t(d.H) * d.W * d.D * 4, stream));
+    // canon word (non-zero = "still canonical") and the voxel->point map (-1 = empty) in one fill
+    GF_CUDA_TRY(cudaMemsetAsync(bp.canon, 0xFF, 256 + size_t(d.H) * d.W * d.D * 4, stream));
+    if (static_cast<long long>(d.N) != static_cast<long long>(d.H) * d.W * d.D)
+        GF_CUDA_TRY(cudaMemsetAsync(bp.canon, 0, 4, stream));
     const long long want = (static_cast<long long>(d.N) + 255) / 256;
     const int grid0 = static_cast<int>(want < 16ll * num_sms ? (want > 0 ? want : 1) : 16ll * num_sms);
     voxel_map_kernel<<<grid0, 256, 0, stream>>>(bp);
@@ -405,6 +416,7 @@ int launch_backward(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_
     bp.v2p = ws.v2p;
     bp.big_list = ws.big_list;
     bp.big_count = ws.big_count;
+    bp.canon = ws.canon;
     bp.aux = ws.aux;
     const bool prob = d.variant == GF_SPLAT_PROB;
 #define GF_CASE(CC)                                                       \

@@ -7,11 +7,14 @@
 //
 //   voxel_map_kernel      voxel -> point index (largest index wins; the reference's write is a race)
 //   backward_small_kernel one warp per Gaussian whose clipped box holds <= kBigBox voxels: lanes
-//                         stride over the box, 28 (+1) partial sums in registers, warp-shuffle
-//                         reduction, plain stores (deterministic).  Larger boxes are queued.
-//   backward_big_kernel   queued Gaussians are split over teams of CTAs sized from the queue
-//                         length (the single whole-grid Gaussian gets every CTA; thousands of large
-//                         Gaussians get one CTA each); block reduction + one atomicAdd per scalar.
+//                         stride over the box (division-free walk, loads one pair ahead, packed
+//                         fp32 pairs for the class sums), 28 (+1) partial sums in registers, one
+//                         transposing warp reduction, plain stores (deterministic).  Larger boxes
+//                         are queued.
+//   backward_big_kernel   queued Gaussians are cut into chunks of kChunkVoxels box voxels (so the work
+//                         is balanced by volume: the whole-grid Gaussian becomes many items, a
+//                         3000-voxel one a single item); CTAs stride over the items; block
+//                         reduction + one atomicAdd per scalar and item.
 #include "common.cuh"
 
 namespace gf {
@@ -24,14 +27,15 @@ struct BwdParams {
     gf_splat_inputs in;
     gf_splat_grads gr;
     int32_t *v2p;      // [H*W*D]
-    int32_t *big_list; // [G]
-    int32_t *big_count;
+    uint2 *work;       // [work_capacity(d)] (Gaussian, chunk) items of the boxes larger than kBigBox
+    int32_t *work_count;
+    int chunk;         // box voxels per work item
     int32_t *canon;    // non-zero after voxel_map_kernel iff N == H*W*D and point n sits in voxel n for all n
     float4 *aux;       // [N] prob only: per-point terms that do not depend on the Gaussian
 };
 
 __global__ void __launch_bounds__(256) voxel_map_kernel(const BwdParams p) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *p.big_count = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_count = 0;
     const int H = p.d.H, W = p.d.W, D = p.d.D;
     for (long long n = blockIdx.x * 256ll + threadIdx.x; n < p.d.N; n += 256ll * gridDim.x) {
         int ix, iy, iz;
@@ -65,45 +69,84 @@ __global__ void __launch_bounds__(256) prob_aux_kernel(const BwdParams p, int C)
     }
 }
 
-// Per-Gaussian constants and running sums of one thread.
+// One (Gaussian, point) pair's point-side data, fetched one iteration ahead of its use.
+template <int C, bool PROB>
+struct PairData {
+    float px, py, pz;
+    float2 up[(C + 1) / 2];   // dL/dlogits[n, :] as packed pairs (zero padded for odd C)
+    float4 ax;                // prob: prob_aux_kernel's per-point terms
+    bool ok;
+};
+
+// Per-Gaussian constants and running sums of one thread.  The sums are kept in the form that needs the
+// fewest instructions per pair; the linear maps to the actual gradients are applied once per Gaussian
+// (finish()):  d(mean) = -A * sum(w d),  d(cov) = -(1/2 | 1) * sum(w d d^T) (+ det terms for prob).
 template <int C, bool PROB>
 struct GaussAcc {
+    static constexpr int CP2 = (C + 1) / 2;
     // constants
-    float mu[3], c6[6], q6[6];  // q6: exponent coefficients pre-scaled by log2(e)
-    float opa, det, norm;
-    float sem[C];
+    float mu[3], q6[6];       // q6: exponent coefficients pre-scaled by log2(e)
+    float opa, norm, inv2det; // prob: kappa*sqrt(det), 0.5/det
+    float2 sem[CP2];
     // sums
-    float sm[3];   // sum w * (A d)
-    float so;      // opacity gradient
-    float ss[C];   // semantics gradient (without the common per-Gaussian factor for the base variant)
-    float sq[6];   // sum w * (dx^2, dy^2, dz^2, dx dy, dy dz, dx dz)
-    float sg;      // prob: sum of gamma
+    float sd[3];      // sum w * d
+    float so;         // opacity gradient
+    float2 ss[CP2];   // semantics gradient (base: without the common factor opa)
+    float sq[6];      // sum w * (dx^2, dy^2, dz^2, dx dy, dy dz, dx dz)
+    float sg;         // prob: sum of gamma
 
     __device__ __forceinline__ void load(const BwdParams &p, int g) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) mu[a] = p.in.means[3 * g + a];
+        float c6[6];
         load_cov6(p.d, p.in.cov, g, c6);
         q6[0] = -0.5f * kLog2e * c6[0]; q6[1] = -0.5f * kLog2e * c6[1]; q6[2] = -0.5f * kLog2e * c6[2];
         q6[3] = -kLog2e * c6[3]; q6[4] = -kLog2e * c6[4]; q6[5] = -kLog2e * c6[5];
         opa = p.in.opacities[g];
-        det = c6[0] * c6[1] * c6[2] + 2.f * c6[3] * c6[4] * c6[5] - c6[0] * c6[4] * c6[4] -
-              c6[1] * c6[5] * c6[5] - c6[2] * c6[3] * c6[3];
-        norm = kKappa * sqrtf(det);
+        if (PROB) {
+            const float det = c6[0] * c6[1] * c6[2] + 2.f * c6[3] * c6[4] * c6[5] - c6[0] * c6[4] * c6[4] -
+                              c6[1] * c6[5] * c6[5] - c6[2] * c6[3] * c6[3];
+            norm = kKappa * sqrtf(det);
+            inv2det = __fdiv_rn(0.5f, det);
+        } else {
+            norm = 0.f; inv2det = 0.f;
+        }
 #pragma unroll
-        for (int k = 0; k < C; ++k) sem[k] = p.in.semantics[static_cast<size_t>(g) * C + k];
+        for (int k = 0; k < CP2; ++k) {
+            sem[k].x = p.in.semantics[static_cast<size_t>(g) * C + 2 * k];
+            sem[k].y = (2 * k + 1 < C) ? p.in.semantics[static_cast<size_t>(g) * C + 2 * k + 1] : 0.f;
+            ss[k] = make_float2(0.f, 0.f);
+        }
 #pragma unroll
-        for (int a = 0; a < 3; ++a) sm[a] = 0.f;
+        for (int a = 0; a < 3; ++a) sd[a] = 0.f;
         so = 0.f; sg = 0.f;
-#pragma unroll
-        for (int k = 0; k < C; ++k) ss[k] = 0.f;
 #pragma unroll
         for (int a = 0; a < 6; ++a) sq[a] = 0.f;
     }
 
-    // contribution of point n (which lies inside the box)
-    __device__ __forceinline__ void visit(const BwdParams &p, long long n) {
-        const float dx = mu[0] - __ldg(p.in.pts + 3 * n), dy = mu[1] - __ldg(p.in.pts + 3 * n + 1),
-                    dz = mu[2] - __ldg(p.in.pts + 3 * n + 2);
+    // issue the loads of point n (n < 0: no point in that voxel)
+    __device__ __forceinline__ void fetch(const BwdParams &p, long long n, PairData<C, PROB> &o) const {
+        o.ok = n >= 0;
+        if (!o.ok) return;
+        o.px = __ldg(p.in.pts + 3 * n); o.py = __ldg(p.in.pts + 3 * n + 1); o.pz = __ldg(p.in.pts + 3 * n + 2);
+        const float *row = p.gr.logits_grad + n * C;
+        if ((C & 1) == 0) {   // rows are 8-byte aligned
+#pragma unroll
+            for (int k = 0; k < CP2; ++k) o.up[k] = __ldg(reinterpret_cast<const float2 *>(row) + k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < CP2; ++k) {
+                o.up[k].x = __ldg(row + 2 * k);
+                o.up[k].y = (2 * k + 1 < C) ? __ldg(row + 2 * k + 1) : 0.f;
+            }
+        }
+        if (PROB) o.ax = __ldg(p.aux + n);
+    }
+
+    // contribution of one pair (the point lies inside the box)
+    __device__ __forceinline__ void consume(const PairData<C, PROB> &d) {
+        if (!d.ok) return;
+        const float dx = mu[0] - d.px, dy = mu[1] - d.py, dz = mu[2] - d.pz;
         float t1 = q6[0] * dx;
         t1 = fmaf(q6[3], dy, t1);
         t1 = fmaf(q6[5], dz, t1);
@@ -114,236 +157,264 @@ struct GaussAcc {
         q = fmaf(q6[2] * dz, dz, q);
         const float E = ex2_approx(q);
         float w;  // weight of the geometric terms: d(loss)/d(power) * E
-        const float2 *up2 = reinterpret_cast<const float2 *>(p.gr.logits_grad + n * C);  // rows are 8B aligned for even C
-        float up[C];
-        if ((C & 1) == 0) {
-#pragma unroll
-            for (int k = 0; k < C / 2; ++k) {
-                const float2 u = __ldg(up2 + k);
-                up[2 * k] = u.x; up[2 * k + 1] = u.y;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < C; ++k) up[k] = __ldg(p.gr.logits_grad + n * C + k);
-        }
         if (!PROB) {
-            // backward.cu:72-87 with t = sum_k sem_k * E * up_k
-            float t = 0.f;
+            // backward.cu:72-87 with t = sum_k sem_k * up_k
+            float2 t = make_float2(0.f, 0.f);
+            const float2 EE = make_float2(E, E);
 #pragma unroll
-            for (int k = 0; k < C; ++k) {
-                const float eu = E * up[k];
-                ss[k] += eu;               // * opa at the end
-                t = fmaf(sem[k], eu, t);
+            for (int k = 0; k < CP2; ++k) {
+                t = __ffma2_rn(sem[k], d.up[k], t);
+                ss[k] = __ffma2_rn(d.up[k], EE, ss[k]);   // * opa at the end
             }
-            so += t;
-            w = opa * t;
+            const float et = E * (t.x + t.y);
+            so += et;
+            w = opa * et;
         } else {
             // localagg_prob/src/backward.cu:76-100 with the point-only terms pre-folded (prob_aux_kernel)
-            const float4 ax = __ldg(p.aux + n);
             const float Pt = norm * E;
             float pi = 0.f;
-            if (ax.w > 0.f) {
-                float u = -ax.x;
-                const float sfac = Pt * opa * ax.w;
+            if (d.ax.w > 0.f) {
+                float2 u2 = make_float2(-d.ax.x, 0.f);
+                const float sfac = Pt * opa * d.ax.w;
+                const float2 ff = make_float2(sfac, sfac);
 #pragma unroll
-                for (int k = 0; k < C; ++k) {
-                    u = fmaf(up[k], sem[k], u);
-                    ss[k] = fmaf(up[k], sfac, ss[k]);
+                for (int k = 0; k < CP2; ++k) {
+                    u2 = __ffma2_rn(d.up[k], sem[k], u2);
+                    ss[k] = __ffma2_rn(d.up[k], ff, ss[k]);
                 }
-                pi = u * opa * ax.w;
-                so = fmaf(u * Pt, ax.w, so);
+                const float u = u2.x + u2.y;
+                pi = u * opa * d.ax.w;
+                so = fmaf(u * Pt, d.ax.w, so);
             }
-            const float eps = pi * norm + __fdiv_rn(ax.y, 1.f - E + 1e-9f) + ax.z;
-            sg += __fdiv_rn(pi * Pt * 0.5f, det);
+            const float eps = pi * norm + __fdividef(d.ax.y, 1.f - E + 1e-9f) + d.ax.z;
+            sg = fmaf(pi * Pt, inv2det, sg);
             w = eps * E;
         }
-        sm[0] = fmaf(w, c6[0] * dx + c6[3] * dy + c6[5] * dz, sm[0]);
-        sm[1] = fmaf(w, c6[3] * dx + c6[1] * dy + c6[4] * dz, sm[1]);
-        sm[2] = fmaf(w, c6[5] * dx + c6[4] * dy + c6[2] * dz, sm[2]);
-        sq[0] = fmaf(w * dx, dx, sq[0]);
-        sq[1] = fmaf(w * dy, dy, sq[1]);
-        sq[2] = fmaf(w * dz, dz, sq[2]);
-        sq[3] = fmaf(w * dx, dy, sq[3]);
-        sq[4] = fmaf(w * dy, dz, sq[4]);
-        sq[5] = fmaf(w * dx, dz, sq[5]);
+        const float wx = w * dx, wy = w * dy, wz = w * dz;
+        sd[0] += wx; sd[1] += wy; sd[2] += wz;
+        sq[0] = fmaf(wx, dx, sq[0]);
+        sq[1] = fmaf(wy, dy, sq[1]);
+        sq[2] = fmaf(wz, dz, sq[2]);
+        sq[3] = fmaf(wx, dy, sq[3]);
+        sq[4] = fmaf(wy, dz, sq[4]);
+        sq[5] = fmaf(wx, dz, sq[5]);
     }
 
-    // number of scalars that travel through reductions: 3 + 1 + C + 6 (+1)
-    static constexpr int kVals = 3 + 1 + C + 6 + (PROB ? 1 : 0);
-    __device__ __forceinline__ float &val(int i) {
-        if (i < 3) return sm[i];
-        if (i == 3) return so;
-        if (i < 4 + C) return ss[i - 4];
-        if (i < 10 + C) return sq[i - 4 - C];
-        return sg;
-    }
-
-    // final gradients from the (fully reduced) sums: means[3], opacity, sem[C], cov[6]
-    __device__ __forceinline__ float grad_means(int a) const { return -sm[a]; }
-    __device__ __forceinline__ float grad_opa() const { return so; }
-    __device__ __forceinline__ float grad_sem(int k) const { return PROB ? ss[k] : opa * ss[k]; }
-    __device__ __forceinline__ float grad_cov(int i) const {
-        float gq = (i < 3) ? -0.5f * sq[i] : -sq[i];
-        if (PROB) {
-            const float a = c6[0], b = c6[1], c = c6[2], d = c6[3], e = c6[4], f = c6[5];
-            const float m[6] = {b * c - e * e, a * c - f * f, a * b - d * d,
-                                2.f * (e * f - c * d), 2.f * (d * f - a * e), 2.f * (d * e - b * f)};
-            gq = fmaf(sg, m[i], gq);
-        }
-        return gq;
+    // The sums as a 32-vector in the order of the output lanes: [0,3) mean, 3 opacity, [4,10) cov,
+    // [10,10+C) semantics, 10+C gamma (prob).  C <= 21.
+    static constexpr int kVals = 10 + C + (PROB ? 1 : 0);
+    static_assert(kVals <= 32, "one lane per reduced value");
+    __device__ __forceinline__ void to_vector(float x[32]) const {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) x[a] = sd[a];
+        x[3] = so;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) x[4 + a] = sq[a];
+#pragma unroll
+        for (int k = 0; k < C; ++k) x[10 + k] = (k & 1) ? ss[k >> 1].y : ss[k >> 1].x;
+        if (PROB) x[10 + C] = sg;
     }
 };
 
-// exact floor(i / n) for 0 <= i < 2^20 given inv_n = fl(1/n): (i+0.5)/n is at least 0.5/n away
-// from an integer while the two roundings perturb it by < 2^20/n * 2^-23 = 0.125/n.
-__device__ __forceinline__ int div_small(int i, float inv_n) {
-    return __float2int_rz((static_cast<float>(i) + 0.5f) * inv_n);
+// Sum of x[i] over the warp for all i at once: afterwards lane L holds the total of x[L] (in x[0]).
+// 31 shuffles instead of 5 per value.
+__device__ __forceinline__ float warp_transpose_reduce(float x[32], int lane) {
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+        const bool upper = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = upper ? x[i] : x[i + h];
+            const float keep = upper ? x[i + h] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return x[0];
 }
 
+// Lane L holds the warp/CTA total of value L (see to_vector).  Applies the per-Gaussian linear maps and
+// writes (or atomically adds) the gradients of Gaussian g.
+template <int C, bool PROB>
+__device__ __forceinline__ void finish(const BwdParams &p, int g, float v, int lane, bool atomic) {
+    const float s0 = __shfl_sync(0xffffffffu, v, 0), s1 = __shfl_sync(0xffffffffu, v, 1), s2 = __shfl_sync(0xffffffffu, v, 2);
+    const float sg = PROB ? __shfl_sync(0xffffffffu, v, 10 + C) : 0.f;
+    float c6[6];
+    load_cov6(p.d, p.in.cov, g, c6);
+    const float a = c6[0], b = c6[1], c = c6[2], d = c6[3], e = c6[4], f = c6[5];
+    float out = 0.f;
+    float *dst = nullptr;   // lane >= 10 + C: nothing to store
+    if (lane < 3) {
+        // -(A * sum w d): rows (a d f), (d b e), (f e c)
+        const float r0 = lane == 0 ? a : (lane == 1 ? d : f);
+        const float r1 = lane == 0 ? d : (lane == 1 ? b : e);
+        const float r2 = lane == 0 ? f : (lane == 1 ? e : c);
+        out = -(r0 * s0 + r1 * s1 + r2 * s2);
+        dst = p.gr.means_grad + 3 * g + lane;
+    } else if (lane == 3) {
+        out = v;
+        dst = p.gr.opacity_grad + g;
+    } else if (lane < 10) {
+        const int i = lane - 4;
+        out = (i < 3) ? -0.5f * v : -v;
+        if (PROB) {
+            const float m[6] = {b * c - e * e, a * c - f * f, a * b - d * d,
+                                2.f * (e * f - c * d), 2.f * (d * f - a * e), 2.f * (d * e - b * f)};
+            float mi = m[0];
+#pragma unroll
+            for (int j = 1; j < 6; ++j) mi = (i == j) ? m[j] : mi;
+            out = fmaf(sg, mi, out);
+        }
+        if (p.d.cov_stride == 9) {
+            // gradient in the layout of the 3x3 input: the six gathered entries [0,4,8,1,5,2] receive it, the
+            // lower triangle gets zero (what indexing autograd produces in the reference, __init__.py:143)
+            const int flat = (i < 3) ? 4 * i : (i == 3 ? 1 : (i == 4 ? 5 : 2));
+            dst = p.gr.cov_grad + 9 * static_cast<size_t>(g) + flat;
+            if (!atomic && i < 3) p.gr.cov_grad[9 * static_cast<size_t>(g) + (i == 0 ? 3 : 5 + i)] = 0.f;
+        } else {
+            dst = p.gr.cov_grad + 6 * static_cast<size_t>(g) + i;
+        }
+    } else if (lane < 10 + C) {
+        out = PROB ? v : p.in.opacities[g] * v;
+        dst = p.gr.semantics_grad + static_cast<size_t>(g) * C + (lane - 10);
+    }
+    if (dst) {
+        if (atomic) atomicAdd(dst, out); else *dst = out;
+    }
+}
+
+// Walks the flat indices first, first+stride, ... < end of a box (z fastest) without a division per
+// step: the stride is decomposed once into (sx, sy, sz) box steps and applied with two carries.
+// Grid voxel indices fit 32 bits (H*W*D < 2^31 is checked at the C ABI).
 struct BoxWalk {
-    int lo[3], nx, ny, nz;
+    int nx, ny, nz;
     long long vol;
-    float inv_nz, inv_ny;
-    bool small_idx;
-    __device__ __forceinline__ void init(const int l[3], const int h[3], bool empty) {
-        lo[0] = l[0]; lo[1] = l[1]; lo[2] = l[2];
+    int vbase;   // grid voxel index of the box corner
+    int WD, D;
+    int ix, iy, iz, sx, sy, sz;
+    int left;    // steps this thread still has to take
+    __device__ __forceinline__ void init(const int l[3], const int h[3], bool empty, int W, int D_) {
         nx = empty ? 0 : h[0] - l[0] + 1;
         ny = empty ? 0 : h[1] - l[1] + 1;
         nz = empty ? 0 : h[2] - l[2] + 1;
         vol = static_cast<long long>(nx) * ny * nz;
-        inv_nz = nz ? __fdiv_rn(1.f, static_cast<float>(nz)) : 0.f;
-        inv_ny = ny ? __fdiv_rn(1.f, static_cast<float>(ny)) : 0.f;
-        small_idx = vol < (1ll << 20);
+        D = D_; WD = W * D_;
+        vbase = empty ? 0 : (l[0] * W + l[1]) * D_ + l[2];
     }
-    // flat box index -> voxel index of the grid
-    __device__ __forceinline__ long long voxel(long long i, int W, int D) const {
-        int ix, iy, iz;
-        if (small_idx) {
-            const int ii = static_cast<int>(i);
-            const int t = div_small(ii, inv_nz);
-            iz = ii - t * nz;
-            ix = div_small(t, inv_ny);
-            iy = t - ix * ny;
-        } else {
-            iz = static_cast<int>(i % nz);
-            const long long t = i / nz;
-            iy = static_cast<int>(t % ny);
-            ix = static_cast<int>(t / ny);
-        }
-        return (static_cast<long long>(lo[0] + ix) * W + (lo[1] + iy)) * D + (lo[2] + iz);
+    __device__ __forceinline__ void start(long long first, long long end, int stride) {
+        if (end > vol) end = vol;
+        left = first < end ? static_cast<int>((end - first + stride - 1) / stride) : 0;
+        if (left == 0) { ix = iy = iz = sx = sy = sz = 0; return; }
+        iz = static_cast<int>(first % nz);
+        const long long t = first / nz;
+        iy = static_cast<int>(t % ny);
+        ix = static_cast<int>(t / ny);
+        sz = stride % nz;
+        const int t2 = stride / nz;
+        sy = t2 % ny;
+        sx = t2 / ny;
+    }
+    __device__ __forceinline__ bool valid() const { return left > 0; }
+    __device__ __forceinline__ int voxel() const { return vbase + ix * WD + iy * D + iz; }
+    __device__ __forceinline__ void step() {
+        --left;
+        iz += sz;
+        const int cz = iz >= nz;
+        iz -= cz ? nz : 0;
+        iy += sy + cz;
+        const int cy = iy >= ny;
+        iy -= cy ? ny : 0;
+        ix += sx + cy;
     }
 };
 
+// The pair loop of one thread, software pipelined by one iteration (the loads of pair i+1 are in
+// flight while pair i is evaluated).
 template <int C, bool PROB>
-__device__ __forceinline__ void store_grads(const BwdParams &p, int g, GaussAcc<C, PROB> &acc, int lane, bool atomic) {
-    // lanes 0..2 means, 3 opacity, 4..9 cov, then semantics over lanes (C <= 32)
-    float v = 0.f;
-    float *dst = nullptr;
-    if (lane < 3) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-            if (lane == a) v = acc.grad_means(a);
-        dst = p.gr.means_grad + 3 * g + lane;
-    } else if (lane == 3) {
-        v = acc.grad_opa();
-        dst = p.gr.opacity_grad + g;
-    } else if (lane < 10) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-            if (lane == 4 + i) v = acc.grad_cov(i);
-        dst = p.gr.cov_grad + 6 * g + (lane - 4);
-    }
-    if (dst) {
-        if (atomic) atomicAdd(dst, v); else *dst = v;
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < C; ++k)
-        if (lane == k) s = acc.grad_sem(k);
-    if (lane < C) {
-        float *d2 = p.gr.semantics_grad + static_cast<size_t>(g) * C + lane;
-        if (atomic) atomicAdd(d2, s); else *d2 = s;
+__device__ __forceinline__ void walk_pairs(const BwdParams &p, GaussAcc<C, PROB> &acc, BoxWalk &box, bool canon) {
+    PairData<C, PROB> pa, pb;
+    auto next = [&](PairData<C, PROB> &o) -> bool {   // false: the walk is over
+        if (!box.valid()) { o.ok = false; return false; }
+        const int v = box.voxel();
+        acc.fetch(p, canon ? v : __ldg(p.v2p + v), o);
+        box.step();
+        return true;
+    };
+    bool more = next(pa);
+    while (more) {
+        more = next(pb);
+        acc.consume(pa);
+        if (!more) { acc.consume(pb); break; }
+        more = next(pa);
+        acc.consume(pb);
+        if (!more) acc.consume(pa);
     }
 }
 
 template <int C, bool PROB>
-__global__ void __launch_bounds__(kBwdThreads) backward_small_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kBwdThreads, 2) backward_small_kernel(const BwdParams p) {
     const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * (kBwdThreads / 32) + (threadIdx.x >> 5);
-    if (g >= p.d.G) return;
+    // no early exit for the warps past G: they redo the last Gaussian and skip the stores, which keeps
+    // every warp provably converged at the shuffles below
+    const int g_raw = blockIdx.x * (kBwdThreads / 32) + (threadIdx.x >> 5);
+    const bool live = g_raw < p.d.G;
+    const int g = live ? g_raw : p.d.G - 1;
     GaussAcc<C, PROB> acc;
     acc.load(p, g);
     int lo[3], hi[3];
     uint32_t err = 0;
-    const bool empty = gaussian_box(p.d, p.in, g, acc.mu, lo, hi, err);
+    const bool empty = gaussian_box(p.d, p.in, g, acc.mu, lo, hi, err) || !live;
     BoxWalk box;
-    box.init(lo, hi, empty);
+    box.init(lo, hi, empty, p.d.W, p.d.D);
     const bool big = box.vol > kBigBox;
     const bool canon = *p.canon != 0;   // then voxel index == point index and the map need not be read
     if (!big) {
-        for (int i = lane; i < static_cast<int>(box.vol); i += 32) {
-            const long long v = box.voxel(i, p.d.W, p.d.D);
-            const long long n = canon ? v : __ldg(p.v2p + v);
-            if (n >= 0) acc.visit(p, n);
-        }
-#pragma unroll
-        for (int i = 0; i < GaussAcc<C, PROB>::kVals; ++i) {
-            float v = acc.val(i);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            acc.val(i) = v;
-        }
-    } else if (lane == 0) {
-        p.big_list[atomicAdd(p.big_count, 1)] = g;
+        box.start(lane, box.vol, 32);
+        walk_pairs<C, PROB>(p, acc, box, canon);
+    } else {
+        const int nch = static_cast<int>((box.vol + p.chunk - 1) / p.chunk);
+        int start = 0;
+        if (lane == 0) start = atomicAdd(p.work_count, nch);
+        start = __shfl_sync(0xffffffffu, start, 0);
+        for (int c = lane; c < nch; c += 32) p.work[start + c] = make_uint2(static_cast<uint32_t>(g), static_cast<uint32_t>(c));
     }
     // small boxes: final values; queued boxes: zeros (the big kernel accumulates atomically)
-    store_grads<C, PROB>(p, g, acc, lane, false);
+    float x[32];
+    acc.to_vector(x);
+    const float v = warp_transpose_reduce(x, lane);
+    finish<C, PROB>(p, g, v, live ? lane : 32, false);
 }
 
 template <int C, bool PROB>
-__global__ void __launch_bounds__(kBwdThreads) backward_big_kernel(const BwdParams p) {
-    const int nbig = *p.big_count;
-    if (nbig == 0) return;
-    const int NB = gridDim.x;
-    const int T = max(1, NB / nbig);        // CTAs per Gaussian
-    const int nteams = NB / T;
-    const int team = blockIdx.x / T, part = blockIdx.x % T;
-    if (team >= nteams) return;
+__global__ void __launch_bounds__(kBwdThreads, 2) backward_big_kernel(const BwdParams p) {
+    const int nwork = *p.work_count;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ float s_part[kBwdThreads / 32][GaussAcc<C, PROB>::kVals];
-    for (int bi = team; bi < nbig; bi += nteams) {
-        const int g = p.big_list[bi];
+    __shared__ float s_part[kBwdThreads / 32][32];
+    const bool canon = *p.canon != 0;
+    for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
+        const uint2 wi = p.work[item];
+        const int g = static_cast<int>(wi.x);
         GaussAcc<C, PROB> acc;
         acc.load(p, g);
         int lo[3], hi[3];
         uint32_t err = 0;
         const bool empty = gaussian_box(p.d, p.in, g, acc.mu, lo, hi, err);
         BoxWalk box;
-        box.init(lo, hi, empty);
-        const long long beg = box.vol * part / T, end = box.vol * (part + 1) / T;
-        const bool canon = *p.canon != 0;
-        for (long long i = beg + threadIdx.x; i < end; i += kBwdThreads) {
-            const long long v = box.voxel(i, p.d.W, p.d.D);
-            const long long n = canon ? v : __ldg(p.v2p + v);
-            if (n >= 0) acc.visit(p, n);
-        }
-#pragma unroll
-        for (int i = 0; i < GaussAcc<C, PROB>::kVals; ++i) {
-            float v = acc.val(i);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_part[warp][i] = v;
-        }
+        box.init(lo, hi, empty, p.d.W, p.d.D);
+        const long long beg = static_cast<long long>(wi.y) * p.chunk;
+        box.start(beg + threadIdx.x, beg + p.chunk, kBwdThreads);
+        walk_pairs<C, PROB>(p, acc, box, canon);
+        float x[32];
+        acc.to_vector(x);
+        const float v = warp_transpose_reduce(x, lane);
+        s_part[warp][lane] = v;
         __syncthreads();
         if (warp == 0) {
+            float tot = 0.f;
 #pragma unroll
-            for (int i = 0; i < GaussAcc<C, PROB>::kVals; ++i) {
-                float v = 0.f;
-#pragma unroll
-                for (int w = 0; w < kBwdThreads / 32; ++w) v += s_part[w][i];
-                acc.val(i) = v;
-            }
-            store_grads<C, PROB>(p, g, acc, lane, true);
+            for (int w = 0; w < kBwdThreads / 32; ++w) tot += s_part[w][lane];
+            finish<C, PROB>(p, g, tot, lane, true);
         }
         __syncthreads();
     }
@@ -353,10 +424,24 @@ __global__ void __launch_bounds__(kBwdThreads) backward_big_kernel(const BwdPara
 // host side
 // ------------------------------------------------------------------------------------------------
 struct BwdWorkspace {
-    int32_t *v2p, *big_list, *big_count, *canon;
+    int32_t *v2p, *work_count, *canon;
+    uint2 *work;
     float4 *aux;
     size_t bytes;
 };
+
+// Box voxels per work item of the big-box kernel, and the worst-case number of items (every Gaussian
+// covers the whole grid).  The chunk grows with the grid so that one Gaussian never needs more than 128 items.
+static int chunk_voxels(const gf_splat_desc &d) {
+    const long long vox = static_cast<long long>(d.H) * d.W * d.D;
+    const long long c = (vox + 127) / 128;
+    return static_cast<int>(c < 4096 ? 4096 : c);
+}
+static size_t work_capacity(const gf_splat_desc &d) {
+    const long long vox = static_cast<long long>(d.H) * d.W * d.D;
+    const long long per = (vox + chunk_voxels(d) - 1) / chunk_voxels(d);
+    return static_cast<size_t>(d.G) * static_cast<size_t>(per > 0 ? per : 1);
+}
 
 static size_t align_up_b(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -368,10 +453,10 @@ void plan_backward_workspace(const gf_splat_desc &d, void *base, BwdWorkspace *w
         off = align_up_b(off + bytes, 256);
         return p;
     };
-    ws->big_count = reinterpret_cast<int32_t *>(take(64));
+    ws->work_count = reinterpret_cast<int32_t *>(take(64));
     ws->canon = reinterpret_cast<int32_t *>(take(256));   // directly in front of v2p: one memset covers both
     ws->v2p = reinterpret_cast<int32_t *>(take(size_t(d.H) * d.W * d.D * 4));
-    ws->big_list = reinterpret_cast<int32_t *>(take(size_t(d.G) * 4));
+    ws->work = reinterpret_cast<uint2 *>(take(work_capacity(d) * sizeof(uint2)));
     ws->aux = reinterpret_cast<float4 *>(take(d.variant == GF_SPLAT_PROB ? size_t(d.N) * 16 : 0));
     ws->bytes = off;
 }
@@ -414,8 +499,9 @@ int launch_backward(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_
     bp.in = in;
     bp.gr = gr;
     bp.v2p = ws.v2p;
-    bp.big_list = ws.big_list;
-    bp.big_count = ws.big_count;
+    bp.work = ws.work;
+    bp.work_count = ws.work_count;
+    bp.chunk = chunk_voxels(d);
     bp.canon = ws.canon;
     bp.aux = ws.aux;
     const bool prob = d.variant == GF_SPLAT_PROB;

@@ -1,0 +1,173 @@
+// The tile walker shared by the forward and backward tile kernels: a CTA owns a bin of 8 x 4 columns x
+// 16 z; it resolves its own ordered Gaussian list from the supertile list (Phase A), streams the
+// records through a shared-memory ring (Phase B) and calls `visit` for every record that touches the
+// calling warp's footprint, in ascending Gaussian order, with all 32 lanes converged.
+#pragma once
+#include "splat_render.cuh"
+
+namespace gf {
+
+#ifndef GF_RENDER_CTAS
+#define GF_RENDER_CTAS 4   // resident CTAs per SM the base tile kernel is compiled for
+#endif
+#ifndef GF_RENDER_VOX
+#define GF_RENDER_VOX 4   // voxels per thread of the tile kernel (2 or 4)
+#endif
+constexpr int kQuadSeg = 512;   // list entries resolved per segment
+constexpr int kBatch = 32;      // records staged per ring slot
+constexpr int kRing = 4;        // ring slots: a warp may run up to kRing-2 batches ahead of the slowest one
+
+template <int C, int VOX>
+struct RenderSmem {
+    static constexpr int REC = rec_floats(C);
+    static constexpr int NT = 512 / VOX;   // threads per CTA: 8 x 4 columns x (16 / VOX) z groups
+    alignas(128) float stage[kRing][kBatch * REC];
+    alignas(8) uint2 list[kQuadSeg + kBatch];  // x: box relative to the bin as bit masks, y: index | warp-hit bits
+    alignas(8) uint64_t bar_full[kRing];       // records of the slot have landed (one cp.async arrival per thread)
+    alignas(8) uint64_t bar_empty[kRing];      // every warp is done with the slot (one arrival per warp)
+    int warp_count[2][NT / 32];
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// the mbarrier receives one arrival from this thread when all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive_on(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_one(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+
+// visit(const float4 *record, uint32_t zbits, bool active): `active` says whether this lane's column lies
+// inside the Gaussian's box; bit v of zbits whether its voxel v does.
+template <int C, int VOX, class Visit>
+__device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, VOX> &sm, int binX0, int binY0, int binZ0,
+                                          uint32_t my_xy, int my_zshift, Visit &&visit) {
+    constexpr int REC = rec_floats(C);
+    constexpr int NT = 512 / VOX, NWARP = NT / 32;
+    constexpr uint32_t VMASK = (1u << VOX) - 1u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = p.d.H, W = p.d.W, D = p.d.D;
+    if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < kRing; ++r) {
+            mbar_init(&sm.bar_full[r], NT);
+            mbar_init(&sm.bar_empty[r], NWARP);
+        }
+        mbar_fence_init();
+    }
+    uint32_t gb = 0;   // batches consumed so far by this CTA: drives ring slots and barrier parities
+    // (the __syncthreads of Phase A below publishes the barrier initialisation)
+
+    // ---- candidates: the ascending list of this bin's supertile ------------------------------------
+    const int st_shift = 31 - __clz(p.st);
+    const int s = (binX0 >> st_shift) * p.nsy + (binY0 >> st_shift);
+    const int ncand = p.counts[s];
+    const int32_t *cand = p.lists + static_cast<size_t>(s) * p.d.G;
+    const uint32_t bX1 = min(binX0 + kBinX, H) - 1, bY1 = min(binY0 + kBinY, W) - 1, bZ1 = min(binZ0 + kBinZ, D) - 1;
+
+    int cpos = 0;
+    while (cpos < ncand) {
+        __syncthreads();   // previous segment fully consumed (and, the first time, barriers initialised)
+        // ======================= Phase A: ordered survivors of the box test ==========================
+        int nlist = 0;
+        while (cpos < ncand && nlist + NT <= kQuadSeg) {
+            constexpr int kPre = 4;   // rounds fetched together (memory-level parallelism)
+            int gg[kPre];
+            uint4 bb[kPre];
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) {
+                const int i = cpos + u * NT + tid;
+                gg[u] = i < ncand ? __ldg(cand + i) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < kPre; ++u)
+                bb[u] = gg[u] >= 0 ? __ldg(reinterpret_cast<const uint4 *>(p.boxes) + gg[u]) : make_uint4(1u, 1u, 1u, 1u);
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) {
+                if (cpos >= ncand || nlist + NT > kQuadSeg) break;   // uniform
+                const uint4 b = bb[u];
+                const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16,
+                               z0 = b.z & 0xffffu, z1 = b.z >> 16;
+                const bool hit = gg[u] >= 0 && x0 <= bX1 && x1 >= static_cast<uint32_t>(binX0) && y0 <= bY1 &&
+                                 y1 >= static_cast<uint32_t>(binY0) && z0 <= bZ1 && z1 >= static_cast<uint32_t>(binZ0) &&
+                                 b.w == 0u;
+                const int rx0 = max(static_cast<int>(x0) - binX0, 0), rx1 = min(static_cast<int>(x1) - binX0, kBinX - 1);
+                const int ry0 = max(static_cast<int>(y0) - binY0, 0), ry1 = min(static_cast<int>(y1) - binY0, kBinY - 1);
+                const int rz0 = max(static_cast<int>(z0) - binZ0, 0), rz1 = min(static_cast<int>(z1) - binZ0, kBinZ - 1);
+                const uint32_t xm = ((2u << rx1) - 1u) & ~((1u << rx0) - 1u);
+                const uint32_t ym = ((2u << ry1) - 1u) & ~((1u << ry0) - 1u);
+                const uint32_t zm = ((2u << rz1) - 1u) & ~((1u << rz0) - 1u);
+                // which warp footprints (x half, z half) does the clipped box touch?
+                uint32_t wh = 0;
+#pragma unroll
+                for (int wq = 0; wq < NWARP; ++wq)
+                    if ((xm & (0xFu << (4 * (wq & 1)))) && (zm & (((1u << (2 * VOX)) - 1u) << (2 * VOX * (wq >> 1))))) wh |= 1u << wq;
+                const uint2 entry = make_uint2(xm | (ym << 8) | (zm << 16), static_cast<uint32_t>(gg[u]) | (wh << 24));
+                const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) sm.warp_count[u & 1][warp] = __popc(ballot);
+                __syncthreads();
+                int off = nlist, total = 0;
+#pragma unroll
+                for (int k = 0; k < NT / 32; ++k) {
+                    const int c = sm.warp_count[u & 1][k];
+                    if (k < warp) off += c;
+                    total += c;
+                }
+                if (hit) sm.list[off + __popc(ballot & lanemask_lt())] = entry;
+                nlist += total;
+                cpos += NT;
+            }
+            __syncthreads();
+        }
+        // pad the last batch with empty entries (no warp-hit bits, so nobody visits them)
+        if (tid < kBatch && nlist + tid < ((nlist + kBatch - 1) / kBatch) * kBatch) sm.list[nlist + tid] = make_uint2(0u, 0u);
+        __syncthreads();
+
+        // ======================= Phase B: stream records and accumulate ==============================
+        // No CTA-wide barrier in this loop: full[] / empty[] mbarriers let the four warps drift apart by
+        // up to kRing-2 batches, so a warp whose footprint is touched by few records does not wait.
+        const int nchunks = (nlist + kBatch - 1) / kBatch;
+        auto issue = [&](int k, uint32_t b_index) {  // batch k of this segment -> ring slot b_index % kRing
+            const int slot = b_index % kRing;
+            const uint32_t use = b_index / kRing;
+            if (use > 0) mbar_wait(&sm.bar_empty[slot], (use - 1) & 1);   // previous occupant released by all warps
+#pragma unroll
+            for (int q = 0; q < (kBatch * 8 + NT - 1) / NT; ++q) {     // 32 records x 8 x 16 B = 256 copies
+                const int piece = tid + NT * q, row = piece >> 3, col = (piece & 7) * 4;
+                if (piece < kBatch * 8 && k * kBatch + row < nlist) {
+                    const uint32_t g = sm.list[k * kBatch + row].y & 0x00FFFFFFu;
+                    cp_async16(&sm.stage[slot][row * REC + col], p.records + static_cast<size_t>(g) * REC + col);
+                }
+            }
+            cp_async_arrive_on(&sm.bar_full[slot]);
+        };
+#pragma unroll 1
+        for (int k = 0; k < kRing - 1 && k < nchunks; ++k) issue(k, gb + k);
+#pragma unroll 1
+        for (int k = 0; k < nchunks; ++k, ++gb) {
+            const int slot = gb % kRing;
+            mbar_wait(&sm.bar_full[slot], (gb / kRing) & 1);
+            {
+            const int half = 0;
+            // records that touch my warp's footprint, in ascending order
+            uint32_t todo = __ballot_sync(0xffffffffu, (sm.list[k * kBatch + half * 32 + lane].y >> (24 + warp)) & 1u);
+            while (todo) {
+                const int j = half * 32 + __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t e = sm.list[k * kBatch + j].x;
+                const uint32_t zb = (e >> my_zshift) & VMASK;
+                visit(reinterpret_cast<const float4 *>(&sm.stage[slot][j * REC]), zb, (e & my_xy) == my_xy && zb != 0u);
+            }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_one(&sm.bar_empty[slot]);       // my warp is done with this slot
+            if (k + kRing - 1 < nchunks) issue(k + kRing - 1, gb + kRing - 1);
+        }
+    }
+
+}
+
+}  // namespace gf

@@ -105,7 +105,7 @@ def splat_forward_raw(desc, pts, means, opa, sem, cov, *, points_int=None, means
 
 def splat_backward_raw(desc, pts, means, opa, sem, cov, grads_in, saved, *, points_int=None, means_int=None,
                        radii=None, scales=None):
-    """One sample through ``gf_splat_backward``.  Returns (g_means[G,3], g_opa[G], g_sem[G,C], g_cov6[G,6])."""
+    """One sample through ``gf_splat_backward``.  Returns (g_means[G,3], g_opa[G], g_sem[G,C], g_cov[G,cov_stride])."""
     L = _lib.lib()
     dev = pts.device
     with torch.cuda.device(dev):
@@ -113,7 +113,7 @@ def splat_backward_raw(desc, pts, means, opa, sem, cov, grads_in, saved, *, poin
         gm = torch.empty((G, 3), dtype=torch.float32, device=dev)
         go = torch.empty((G,), dtype=torch.float32, device=dev)
         gs = torch.empty((G, C), dtype=torch.float32, device=dev)
-        gc = torch.empty((G, 6), dtype=torch.float32, device=dev)
+        gc = torch.empty((G, desc.cov_stride), dtype=torch.float32, device=dev)
         ws_bytes = L.gf_splat_backward_workspace_bytes(ctypes.byref(desc))
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         ins = SplatInputs(_ptr(pts), _ptr(points_int), _ptr(means), _ptr(means_int), _ptr(opa), _ptr(sem), _ptr(cov),
@@ -186,12 +186,11 @@ class _SplatFunction(torch.autograd.Function):
         else:
             pts, means, opa, sem, scales, cov = ctx.saved_tensors
             grads_in, saved = (_f32c(grad_outputs[0]), None, None), (None, None, None)
-        gm, go, gs, gc6 = splat_backward_raw(ctx.desc, pts, means, opa, sem, cov, grads_in, saved, scales=scales)
-        # the 6 gathered entries receive gradient, the rest of the 3x3 gets zero (indexing autograd
-        # in the reference: cov3D.flatten(1)[:, [0,4,8,1,5,2]])
-        gcov = torch.zeros((gc6.shape[0], 9), dtype=torch.float32, device=gc6.device)
-        gcov[:, list(_COV_IDX)] = gc6
-        return None, gm, go, gs, None, gcov.reshape(-1, 3, 3), None
+        # cov_stride is 9 here: the kernel writes the gradient straight into the 3x3 layout (the six gathered
+        # entries carry it, the lower triangle is zero -- indexing autograd in the reference:
+        # cov3D.flatten(1)[:, [0,4,8,1,5,2]])
+        gm, go, gs, gcov = splat_backward_raw(ctx.desc, pts, means, opa, sem, cov, grads_in, saved, scales=scales)
+        return None, gm, go, gs, None, gcov.view(-1, 3, 3), None
 
 
 class _LocalAggregatorBase(nn.Module):

@@ -115,7 +115,8 @@ typedef struct gf_splat_grads {
     float *means_grad;            /* [G,3] */
     float *opacity_grad;          /* [G] */
     float *semantics_grad;        /* [G,C] */
-    float *cov_grad;              /* [G,6] in (xx,yy,zz,xy,yz,xz) order */
+    float *cov_grad;              /* cov_stride 6: [G,6] in (xx,yy,zz,xy,yz,xz) order; cov_stride 9: [G,9] row-major
+                                     3x3, entries [0,4,8,1,5,2] carry the gradient, [3,6,7] are written as 0 */
 } gf_splat_grads;
 
 typedef struct gf_daf_desc {

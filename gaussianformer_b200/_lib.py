@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_size_t, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgf_b200.so")
+# GF_B200_LIB: developer override to A/B an alternative build of the same library (tools/build_variant.py)
+LIB_PATH = os.environ.get("GF_B200_LIB") or os.path.join(_HERE, "csrc", "libgf_b200.so")
 
 GF_OK = 0
 GF_SPLAT_BASE, GF_SPLAT_PROB = 0, 1

@@ -27,7 +27,7 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(HERE, f) for f in SOURCES + ["common.cuh", "splat_render.cuh"]] + [os.path.join(ROOT, "include", "gf_b200.h")]
+    deps = [os.path.join(HERE, f) for f in SOURCES + ["common.cuh", "splat_render.cuh", "splat_tile.cuh"]] + [os.path.join(ROOT, "include", "gf_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -20,7 +20,14 @@
 namespace gf {
 
 constexpr int kBigBox = 2048;
-constexpr int kBwdThreads = 256;
+// CTA shapes of the two pair kernels: the prob variant carries more per-thread state, so it trades resident
+// warps for registers (128 threads x 3 CTAs -> 168 registers) instead of spilling at 128.
+#ifndef GF_BWD_PROB_THREADS
+#define GF_BWD_PROB_THREADS 128
+#define GF_BWD_PROB_CTAS 3
+#endif
+constexpr int bwd_threads(bool prob) { return prob ? GF_BWD_PROB_THREADS : 256; }
+constexpr int bwd_ctas(bool prob) { return prob ? GF_BWD_PROB_CTAS : 2; }
 
 struct BwdParams {
     gf_splat_desc d;
@@ -72,10 +79,26 @@ __global__ void __launch_bounds__(256) prob_aux_kernel(const BwdParams p, int C)
 // One (Gaussian, point) pair's point-side data, fetched one iteration ahead of its use.
 template <int C, bool PROB>
 struct PairData {
+    static constexpr int CP2 = (C + 1) / 2;
+    static constexpr int kVec = (C + 2 + 3) / 4;   // float4 loads that cover a row starting 0 or 8 bytes into the first
     float px, py, pz;
-    float2 up[(C + 1) / 2];   // dL/dlogits[n, :] as packed pairs (zero padded for odd C)
+    // dL/dlogits[n, :].  Wide mode (even C, 16-byte aligned base): the kVec aligned float4 that contain the
+    // row, which starts at float `2*shift` of them -- a warp's 32 rows of 4C bytes then cost kVec
+    // L1 passes instead of C/2.  Otherwise: packed pairs (zero padded for odd C) in raw[k/2].
+    float4 raw[kVec];
+    bool shift;
     float4 ax;                // prob: prob_aux_kernel's per-point terms
     bool ok;
+    template <bool WIDE>
+    __device__ __forceinline__ float2 up(int k) const {   // k is a compile-time constant after unrolling
+        if (WIDE) {
+            const float2 a = (k & 1) ? make_float2(raw[k >> 1].z, raw[k >> 1].w) : make_float2(raw[k >> 1].x, raw[k >> 1].y);
+            const int k1 = k + 1;
+            const float2 b = (k1 & 1) ? make_float2(raw[k1 >> 1].z, raw[k1 >> 1].w) : make_float2(raw[k1 >> 1].x, raw[k1 >> 1].y);
+            return shift ? b : a;
+        }
+        return (k & 1) ? make_float2(raw[k >> 1].z, raw[k >> 1].w) : make_float2(raw[k >> 1].x, raw[k >> 1].y);
+    }
 };
 
 // Per-Gaussian constants and running sums of one thread.  The sums are kept in the form that needs the
@@ -125,25 +148,47 @@ struct GaussAcc {
     }
 
     // issue the loads of point n (n < 0: no point in that voxel)
+    template <bool WIDE>
     __device__ __forceinline__ void fetch(const BwdParams &p, long long n, PairData<C, PROB> &o) const {
         o.ok = n >= 0;
         if (!o.ok) return;
         o.px = __ldg(p.in.pts + 3 * n); o.py = __ldg(p.in.pts + 3 * n + 1); o.pz = __ldg(p.in.pts + 3 * n + 2);
         const float *row = p.gr.logits_grad + n * C;
-        if ((C & 1) == 0) {   // rows are 8-byte aligned
+        if (WIDE) {
+            // 4C bytes starting 8-byte aligned: the enclosing 16-byte aligned window of kVec float4
+            o.shift = (reinterpret_cast<uintptr_t>(row) & 8) != 0;
+            const float4 *w = reinterpret_cast<const float4 *>(row - (o.shift ? 2 : 0));
 #pragma unroll
-            for (int k = 0; k < CP2; ++k) o.up[k] = __ldg(reinterpret_cast<const float2 *>(row) + k);
+            for (int k = 0; k < PairData<C, PROB>::kVec - 1; ++k) o.raw[k] = __ldg(w + k);
+            constexpr int last = PairData<C, PROB>::kVec - 1;
+            // the last float4 of an unshifted row may reach past the row; past the tensor for the last row
+            if ((C % 4) == 2 && !o.shift && n + 1 >= p.d.N) {
+                const float2 t = __ldg(reinterpret_cast<const float2 *>(w + last));
+                o.raw[last] = make_float4(t.x, t.y, 0.f, 0.f);
+            } else if ((C % 4) == 0 && !o.shift) {
+                o.raw[last] = make_float4(0.f, 0.f, 0.f, 0.f);   // C % 4 == 0: the unshifted row ends with float4 last-1
+            } else {
+                o.raw[last] = __ldg(w + last);
+            }
+        } else if ((C & 1) == 0 && (reinterpret_cast<uintptr_t>(p.gr.logits_grad) & 7) == 0) {   // rows are 8-byte aligned
+#pragma unroll
+            for (int k = 0; k < CP2; ++k) {
+                const float2 t = __ldg(reinterpret_cast<const float2 *>(row) + k);
+                if (k & 1) { o.raw[k >> 1].z = t.x; o.raw[k >> 1].w = t.y; } else { o.raw[k >> 1].x = t.x; o.raw[k >> 1].y = t.y; }
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < CP2; ++k) {
-                o.up[k].x = __ldg(row + 2 * k);
-                o.up[k].y = (2 * k + 1 < C) ? __ldg(row + 2 * k + 1) : 0.f;
+                const float a = __ldg(row + 2 * k);
+                const float b = (2 * k + 1 < C) ? __ldg(row + 2 * k + 1) : 0.f;
+                if (k & 1) { o.raw[k >> 1].z = a; o.raw[k >> 1].w = b; } else { o.raw[k >> 1].x = a; o.raw[k >> 1].y = b; }
             }
         }
         if (PROB) o.ax = __ldg(p.aux + n);
     }
 
     // contribution of one pair (the point lies inside the box)
+    template <bool WIDE>
     __device__ __forceinline__ void consume(const PairData<C, PROB> &d) {
         if (!d.ok) return;
         const float dx = mu[0] - d.px, dy = mu[1] - d.py, dz = mu[2] - d.pz;
@@ -163,8 +208,9 @@ struct GaussAcc {
             const float2 EE = make_float2(E, E);
 #pragma unroll
             for (int k = 0; k < CP2; ++k) {
-                t = __ffma2_rn(sem[k], d.up[k], t);
-                ss[k] = __ffma2_rn(d.up[k], EE, ss[k]);   // * opa at the end
+                const float2 u = d.template up<WIDE>(k);
+                t = __ffma2_rn(sem[k], u, t);
+                ss[k] = __ffma2_rn(u, EE, ss[k]);   // * opa at the end
             }
             const float et = E * (t.x + t.y);
             so += et;
@@ -179,8 +225,9 @@ struct GaussAcc {
                 const float2 ff = make_float2(sfac, sfac);
 #pragma unroll
                 for (int k = 0; k < CP2; ++k) {
-                    u2 = __ffma2_rn(d.up[k], sem[k], u2);
-                    ss[k] = __ffma2_rn(d.up[k], ff, ss[k]);
+                    const float2 uk = d.template up<WIDE>(k);
+                    u2 = __ffma2_rn(uk, sem[k], u2);
+                    ss[k] = __ffma2_rn(uk, ff, ss[k]);
                 }
                 const float u = u2.x + u2.y;
                 pi = u * opa * d.ax.w;
@@ -331,29 +378,42 @@ struct BoxWalk {
 
 // The pair loop of one thread, software pipelined by one iteration (the loads of pair i+1 are in
 // flight while pair i is evaluated).
-template <int C, bool PROB>
-__device__ __forceinline__ void walk_pairs(const BwdParams &p, GaussAcc<C, PROB> &acc, BoxWalk &box, bool canon) {
+template <int C, bool PROB, bool WIDE>
+__device__ __forceinline__ void walk_pairs_t(const BwdParams &p, GaussAcc<C, PROB> &acc, BoxWalk &box, bool canon) {
     PairData<C, PROB> pa, pb;
     auto next = [&](PairData<C, PROB> &o) -> bool {   // false: the walk is over
         if (!box.valid()) { o.ok = false; return false; }
         const int v = box.voxel();
-        acc.fetch(p, canon ? v : __ldg(p.v2p + v), o);
+        acc.template fetch<WIDE>(p, canon ? v : __ldg(p.v2p + v), o);
         box.step();
         return true;
     };
     bool more = next(pa);
     while (more) {
         more = next(pb);
-        acc.consume(pa);
-        if (!more) { acc.consume(pb); break; }
+        acc.template consume<WIDE>(pa);
+        if (!more) { acc.template consume<WIDE>(pb); break; }
         more = next(pa);
-        acc.consume(pb);
-        if (!more) acc.consume(pa);
+        acc.template consume<WIDE>(pb);
+        if (!more) acc.template consume<WIDE>(pa);
     }
 }
 
+#ifndef GF_BWD_WIDE
+#define GF_BWD_WIDE 1
+#endif
 template <int C, bool PROB>
-__global__ void __launch_bounds__(kBwdThreads, 2) backward_small_kernel(const BwdParams p) {
+__device__ __forceinline__ void walk_pairs(const BwdParams &p, GaussAcc<C, PROB> &acc, BoxWalk &box, bool canon) {
+    // wide rows need an even class count and a 16-byte aligned gradient tensor (uniform for the launch)
+    if (GF_BWD_WIDE && (C & 1) == 0 && (reinterpret_cast<uintptr_t>(p.gr.logits_grad) & 15) == 0)
+        walk_pairs_t<C, PROB, true>(p, acc, box, canon);
+    else
+        walk_pairs_t<C, PROB, false>(p, acc, box, canon);
+}
+
+template <int C, bool PROB>
+__global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_small_kernel(const BwdParams p) {
+    constexpr int kBwdThreads = bwd_threads(PROB);
     const int lane = threadIdx.x & 31;
     // no early exit for the warps past G: they redo the last Gaussian and skip the stores, which keeps
     // every warp provably converged at the shuffles below
@@ -387,7 +447,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) backward_small_kernel(const Bw
 }
 
 template <int C, bool PROB>
-__global__ void __launch_bounds__(kBwdThreads, 2) backward_big_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_big_kernel(const BwdParams p) {
+    constexpr int kBwdThreads = bwd_threads(PROB);
     const int nwork = *p.work_count;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ float s_part[kBwdThreads / 32][32];
@@ -482,10 +543,11 @@ static int launch_backward_t(const BwdParams &bp, int num_sms, cudaStream_t stre
         prob_aux_kernel<<<grid0, 256, 0, stream>>>(bp, C);
         GF_CUDA_TRY(cudaGetLastError());
     }
+    constexpr int kBwdThreads = bwd_threads(PROB);
     const int per_cta = kBwdThreads / 32;
     backward_small_kernel<C, PROB><<<(d.G + per_cta - 1) / per_cta, kBwdThreads, 0, stream>>>(bp);
     GF_CUDA_TRY(cudaGetLastError());
-    backward_big_kernel<C, PROB><<<num_sms * 4, kBwdThreads, 0, stream>>>(bp);
+    backward_big_kernel<C, PROB><<<num_sms * bwd_ctas(PROB) * 2, kBwdThreads, 0, stream>>>(bp);
     GF_CUDA_TRY(cudaGetLastError());
     return GF_OK;
 }

@@ -26,8 +26,6 @@ extern thread_local cudaEvent_t g_ev_before, g_ev_after;  // measurement hooks (
 //     voxels with one shift, and the class accumulation runs on packed fp32 pairs (FFMA2).
 template <int C, bool PROB, int VOX>
 __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CTAS) : (PROB ? 2 : 3)) render_tile_kernel(const RenderParams p) {
-    constexpr int NT = 512 / VOX, NWARP = NT / 32;
-    constexpr uint32_t VMASK = (1u << VOX) - 1u;
     constexpr int REC = rec_floats(C);
     constexpr int CP2 = (C + 1) / 2;   // packed class pairs
     static_assert(REC == 32, "one record = 128 bytes");
@@ -219,7 +217,6 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
         for (int v = 0; v < VOX; ++v)
 #pragma unroll
             for (int c = 0; c < C; ++c) flat[v * C + c] = out[v][c];
-#pragma unroll
         if constexpr ((VOX * C) % 4 == 0) {      // n0 * C * 4 bytes is then a multiple of 16
 #pragma unroll
             for (int i = 0; i < VOX * C / 4; ++i)

@@ -102,6 +102,31 @@ def test_generic_points_path():
     h.assert_close(out2.cpu().numpy(), ref2["logits"], what="permuted logits")
 
 
+def test_backward_generic_points_and_unaligned_gradients():
+    """Backward paths off the fast lane: points not in voxel order (voxel -> point map), a subset of the grid
+    (empty voxels), and upstream gradients whose storage is only 4- or 8-byte aligned (narrow row loads)."""
+    import oracle
+    kw, inp, variant = h.splat_case("tiny", 11, True)
+    gen = torch.Generator().manual_seed(3)
+    pts = inp["pts"][0]
+    perm = torch.randperm(pts.shape[0], generator=gen)
+    for idx, offset in ((perm, 0), (perm[: pts.shape[0] // 2], 0), (torch.arange(pts.shape[0]), 1),
+                        (torch.arange(pts.shape[0]), 2)):
+        inp2 = dict(inp, pts=pts[idx][None].contiguous())
+        _, t, out = _run(kw, inp2, variant, requires_grad=True)
+        g = torch.randn(out.shape, generator=gen)
+        flat = torch.empty(g.numel() + offset, device="cuda")
+        g_dev = flat[offset:].view_as(g)          # storage offset of `offset` floats
+        g_dev.copy_(g)
+        assert g_dev.data_ptr() % 16 == 4 * offset
+        out.backward(g_dev)
+        gm, go, gs, gc = h.oracle_backward(kw, inp2, variant, (g.numpy(),))
+        for name, mine, ref in (("means", t["means"].grad[0], gm), ("opa", t["opa"].grad[0], go),
+                                ("sem", t["sem"].grad[0], gs), ("cov", t["cov"].grad[0], oracle.cov6_grad_to_3x3(gc))):
+            h.assert_close(mine.cpu().numpy(), ref, rtol=1e-3, atol=h.grad_tolerance(ref),
+                           what=f"grad {name} (N={len(idx)}, offset={offset})")
+
+
 def test_reference_asserts_are_raised():
     kw, inp, variant = h.splat_case("tiny", 0)
     bad = dict(inp, means=inp["means"].clone())

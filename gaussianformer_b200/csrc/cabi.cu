@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gf {
@@ -43,6 +45,14 @@ int launch_daf_backward(const gf_daf_desc &d, const float *feat, const int32_t *
                         float *grad_loc, float *grad_weights, int num_sms, cudaStream_t stream);
 
 thread_local cudaEvent_t g_ev_before = nullptr, g_ev_after = nullptr;
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("GF_B200_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 static int num_sms_of_current_device(int *out) {
     static int cached[64];

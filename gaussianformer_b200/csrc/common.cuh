@@ -72,6 +72,25 @@ constexpr int kPackThreads = 64;   // small CTAs: ~400 of them cover the 148 SMs
 // device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+// Launches `kernel` so that it may become resident while the preceding kernel of the stream is still
+// running (programmatic stream serialization).  The kernel must call pdl_wait() before it touches
+// anything the preceding kernel writes.  GF_B200_PDL=0 falls back to plain stream order.
+bool pdl_enabled();
+template <class Params>
+cudaError_t launch_chained(void (*kernel)(Params), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Params &p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -122,6 +141,13 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+
+// Programmatic dependent launch (the three kernels of a forward call are chained with it, see
+// launch_chained): launch_dependents lets the next kernel of the stream become resident while this grid
+// is still running; wait blocks until the preceding grid has completed and its writes are visible.
+// Both are no-ops for a kernel launched without the attribute / without a dependent.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;

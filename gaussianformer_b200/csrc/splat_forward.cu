@@ -98,7 +98,6 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
                 }
                 if (!(ix == X && iy == Y && iz == Z0 + v)) stray |= 1u << v;
             }
-        if (stray) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
     }
     // do my VOX points share x and y exactly?  (decided once; the branch on it is warp-uniform in practice)
     bool column = true;
@@ -117,6 +116,10 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
         zsum[v] = 0.f; dens[v] = 0.f; keep[v] = 1.f;
     }
 
+    // Everything above depends on the caller's inputs only; the records, boxes, lists and the status word
+    // come from the two preparation kernels, which this grid may have been launched ahead of.
+    pdl_wait();
+    if (stray) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
     walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, [&](const float4 *r4, uint32_t zb, bool active) {
         if (active) {
                     const float4 g0 = r4[0], g1 = r4[1];
@@ -308,7 +311,11 @@ static int launch_render_t(const RenderParams &rp, bool tile_path, int num_sms, 
             render_tile_kernel<C, PROB, 2><<<grid, 256, sizeof(RenderSmem<C, 2>), stream>>>(rp);
         else
 #endif
+        if (g_ev_before && g_ev_after) {   // kernel timed alone: plain stream order
             render_tile_kernel<C, PROB, 4><<<grid, 128, sizeof(RenderSmem<C, 4>), stream>>>(rp);
+        } else {
+            GF_CUDA_TRY(launch_chained(render_tile_kernel<C, PROB, 4>, grid, dim3(128), sizeof(RenderSmem<C, 4>), stream, rp));
+        }
         GF_CUDA_TRY(cudaGetLastError());
         if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_after, stream));
         return GF_OK;   // stray points were handled inside the tile kernel

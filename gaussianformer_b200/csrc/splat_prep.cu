@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool live = g < p.d.G;
     if (threadIdx.x == 0) s_err = 0;
+    pdl_launch_dependents();   // the list kernel may become resident now; it waits for this grid before reading
 
     uint32_t err = 0;
     int lo[3] = {1, 1, 1}, hi[3] = {0, 0, 0};
@@ -155,6 +156,8 @@ __global__ void __launch_bounds__(kListThreads) list_kernel(const ListParams p) 
     int32_t *list = p.lists + static_cast<size_t>(s) * p.G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int s_warp[2][kListThreads / 32];
+    pdl_launch_dependents();   // lets the render kernel start its point prologue
+    pdl_wait();                // masks and flags of the pack kernel are complete from here on
     int base = 0, pass = 0;
     for (int w0 = 0; w0 < p.nwords; w0 += kListThreads * kListWordsPerThread, ++pass) {
         const int first = w0 + threadIdx.x * kListWordsPerThread;
@@ -279,8 +282,7 @@ int launch_prep(const gf_splat_desc &d, const gf_splat_inputs &in, const SplatWo
     lp.G = d.G;
     lp.pack_ctas = ws.pack_ctas;
     lp.initial_flags = initial_flags;
-    list_kernel<<<ws.nsuper, kListThreads, 0, stream>>>(lp);
-    GF_CUDA_TRY(cudaGetLastError());
+    GF_CUDA_TRY(launch_chained(list_kernel, dim3(ws.nsuper), dim3(kListThreads), 0, stream, lp));
     return GF_OK;
 }
 

@@ -394,6 +394,20 @@ def side_measurements(dev, kw, inp0, resident, desc):
         mp.validate = False
         tp = {k: v.to(dev) for k, v in inpp.items()}
         out["prob_gs6400_fwd_ms"] = timeit(lambda: mp(tp["pts"], tp["means"], tp["opa"], tp["sem"], tp["scales"], tp["cov"]), reps=10)
+        for k in ("means", "opa", "sem", "cov"):
+            tp[k].requires_grad_(True)
+        lg, bl, de = mp(tp["pts"], tp["means"], tp["opa"], tp["sem"], tp["scales"], tp["cov"])
+        gp = [torch.randn_like(lg), torch.randn_like(bl), torch.randn_like(de)]
+        out["prob_gs6400_bwd_ms"] = timeit(lambda: torch.autograd.grad([lg, bl, de], [tp["means"], tp["opa"], tp["sem"], tp["cov"]],
+                                                                       gp, retain_graph=True), reps=5)
+        del lg, bl, de, gp, tp
+        # BASELINE.json configs[2]: 144 000 Gaussians into the same grid (forward, voxel-centre points)
+        kwl, inpl, _ = make_splat_inputs("gs144000", seed=0, perturb=False)
+        ml = LocalAggregator(**kwl).to(dev)
+        ml.validate = False
+        tl = {k: v.to(dev) for k, v in inpl.items()}
+        out["gs144000_fwd_ms"] = timeit(lambda: ml(tl["pts"], tl["means"], tl["opa"], tl["sem"], tl["scales"], tl["cov"]), reps=10)
+        del tl
         fms, loc, w = make_daf_inputs(seed=0)
         feat, shape, start = DAF.feature_maps_format([f.to(dev) for f in fms])
         feat = feat.contiguous()

@@ -11,10 +11,11 @@
 //                         fp32 pairs for the class sums), 28 (+1) partial sums in registers, one
 //                         transposing warp reduction, plain stores (deterministic).  Larger boxes
 //                         are queued.
-//   backward_big_kernel   queued Gaussians are cut into chunks of kChunkVoxels box voxels (so the work
-//                         is balanced by volume: the whole-grid Gaussian becomes many items, a
-//                         3000-voxel one a single item); CTAs stride over the items; block
-//                         reduction + one atomicAdd per scalar and item.
+//   backward_big_kernel   the queued boxes, measured in chunks of kBigChunk box voxels, form one long
+//                         line of work; every CTA takes an equal contiguous span of it (balanced by
+//                         volume: the whole-grid Gaussian is spread over the whole GPU, while a span
+//                         of small queued boxes is walked Gaussian by Gaussian); block reduction +
+//                         one atomicAdd per scalar and (CTA, Gaussian) segment.
 #include "common.cuh"
 
 namespace gf {
@@ -34,15 +35,15 @@ struct BwdParams {
     gf_splat_inputs in;
     gf_splat_grads gr;
     int32_t *v2p;      // [H*W*D]
-    uint2 *work;       // [work_capacity(d)] (Gaussian, chunk) items of the boxes larger than kBigBox
-    int32_t *work_count;
-    int chunk;         // box voxels per work item
+    uint2 *big;        // [G] queue of the boxes larger than kBigBox: (Gaussian, first chunk), ascending in both
+    unsigned long long *big_ctr;   // queue length << 40 | chunks queued (one atomic keeps the two in step)
+    int chunk;         // box voxels per chunk
     int32_t *canon;    // non-zero after voxel_map_kernel iff N == H*W*D and point n sits in voxel n for all n
     float4 *aux;       // [N] prob only: per-point terms that do not depend on the Gaussian
 };
 
 __global__ void __launch_bounds__(256) voxel_map_kernel(const BwdParams p) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_count = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.big_ctr = 0ull;
     const int H = p.d.H, W = p.d.W, D = p.d.D;
     for (long long n = blockIdx.x * 256ll + threadIdx.x; n < p.d.N; n += 256ll * gridDim.x) {
         int ix, iy, iz;
@@ -433,11 +434,11 @@ __global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_sm
         box.start(lane, box.vol, 32);
         walk_pairs<C, PROB>(p, acc, box, canon);
     } else {
-        const int nch = static_cast<int>((box.vol + p.chunk - 1) / p.chunk);
-        int start = 0;
-        if (lane == 0) start = atomicAdd(p.work_count, nch);
-        start = __shfl_sync(0xffffffffu, start, 0);
-        for (int c = lane; c < nch; c += 32) p.work[start + c] = make_uint2(static_cast<uint32_t>(g), static_cast<uint32_t>(c));
+        if (lane == 0) {
+            const unsigned long long nch = static_cast<unsigned long long>((box.vol + p.chunk - 1) / p.chunk);
+            const unsigned long long old = atomicAdd(p.big_ctr, (1ull << 40) | nch);
+            p.big[old >> 40] = make_uint2(static_cast<uint32_t>(g), static_cast<uint32_t>(old & ((1ull << 40) - 1)));
+        }
     }
     // small boxes: final values; queued boxes: zeros (the big kernel accumulates atomically)
     float x[32];
@@ -449,22 +450,34 @@ __global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_sm
 template <int C, bool PROB>
 __global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_big_kernel(const BwdParams p) {
     constexpr int kBwdThreads = bwd_threads(PROB);
-    const int nwork = *p.work_count;
+    const unsigned long long ctr = *p.big_ctr;
+    const int nbig = static_cast<int>(ctr >> 40);
+    const long long total = static_cast<long long>(ctr & ((1ull << 40) - 1));
+    if (nbig == 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ float s_part[kBwdThreads / 32][32];
     const bool canon = *p.canon != 0;
-    for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
-        const uint2 wi = p.work[item];
-        const int g = static_cast<int>(wi.x);
+    // my span of the chunk line, and the queue entry its first chunk belongs to (last entry with first <= lo)
+    long long lo = total * blockIdx.x / gridDim.x;
+    const long long hi = total * (blockIdx.x + 1) / gridDim.x;
+    if (lo >= hi) return;
+    int e = 0;
+    for (int step = 1 << (31 - __clz(nbig)); step > 0; step >>= 1)
+        if (e + step < nbig && static_cast<long long>(p.big[e + step].y) <= lo) e += step;
+    for (; lo < hi; ++e) {
+        const uint2 q = p.big[e];
+        const int g = static_cast<int>(q.x);
+        const long long next = (e + 1 < nbig) ? static_cast<long long>(p.big[e + 1].y) : total;
+        const long long seg_end = next < hi ? next : hi;
         GaussAcc<C, PROB> acc;
         acc.load(p, g);
-        int lo[3], hi[3];
+        int blo[3], bhi[3];
         uint32_t err = 0;
-        const bool empty = gaussian_box(p.d, p.in, g, acc.mu, lo, hi, err);
+        const bool empty = gaussian_box(p.d, p.in, g, acc.mu, blo, bhi, err);
         BoxWalk box;
-        box.init(lo, hi, empty, p.d.W, p.d.D);
-        const long long beg = static_cast<long long>(wi.y) * p.chunk;
-        box.start(beg + threadIdx.x, beg + p.chunk, kBwdThreads);
+        box.init(blo, bhi, empty, p.d.W, p.d.D);
+        const long long beg = (lo - q.y) * p.chunk;
+        box.start(beg + threadIdx.x, (seg_end - q.y) * p.chunk, kBwdThreads);
         walk_pairs<C, PROB>(p, acc, box, canon);
         float x[32];
         acc.to_vector(x);
@@ -478,6 +491,7 @@ __global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_bi
             finish<C, PROB>(p, g, tot, lane, true);
         }
         __syncthreads();
+        lo = seg_end;
     }
 }
 
@@ -485,23 +499,20 @@ __global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_bi
 // host side
 // ------------------------------------------------------------------------------------------------
 struct BwdWorkspace {
-    int32_t *v2p, *work_count, *canon;
-    uint2 *work;
+    int32_t *v2p, *canon;
+    unsigned long long *big_ctr;
+    uint2 *big;
     float4 *aux;
     size_t bytes;
 };
 
-// Box voxels per work item of the big-box kernel, and the worst-case number of items (every Gaussian
-// covers the whole grid).  The chunk grows with the grid so that one Gaussian never needs more than 128 items.
+// Box voxels per chunk of the big-box kernel: 4 passes of a 256-thread CTA, grown when needed so that
+// the chunk line of the worst case (every Gaussian covers the whole grid) stays below 2^31 chunks.
 static int chunk_voxels(const gf_splat_desc &d) {
     const long long vox = static_cast<long long>(d.H) * d.W * d.D;
-    const long long c = (vox + 127) / 128;
-    return static_cast<int>(c < 4096 ? 4096 : c);
-}
-static size_t work_capacity(const gf_splat_desc &d) {
-    const long long vox = static_cast<long long>(d.H) * d.W * d.D;
-    const long long per = (vox + chunk_voxels(d) - 1) / chunk_voxels(d);
-    return static_cast<size_t>(d.G) * static_cast<size_t>(per > 0 ? per : 1);
+    long long c = 1024;
+    while ((vox + c - 1) / c * static_cast<long long>(d.G > 0 ? d.G : 1) >= (1ll << 31)) c *= 2;
+    return static_cast<int>(c);
 }
 
 static size_t align_up_b(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -514,10 +525,10 @@ void plan_backward_workspace(const gf_splat_desc &d, void *base, BwdWorkspace *w
         off = align_up_b(off + bytes, 256);
         return p;
     };
-    ws->work_count = reinterpret_cast<int32_t *>(take(64));
+    ws->big_ctr = reinterpret_cast<unsigned long long *>(take(64));
     ws->canon = reinterpret_cast<int32_t *>(take(256));   // directly in front of v2p: one memset covers both
     ws->v2p = reinterpret_cast<int32_t *>(take(size_t(d.H) * d.W * d.D * 4));
-    ws->work = reinterpret_cast<uint2 *>(take(work_capacity(d) * sizeof(uint2)));
+    ws->big = reinterpret_cast<uint2 *>(take(size_t(d.G) * sizeof(uint2)));
     ws->aux = reinterpret_cast<float4 *>(take(d.variant == GF_SPLAT_PROB ? size_t(d.N) * 16 : 0));
     ws->bytes = off;
 }
@@ -561,8 +572,8 @@ int launch_backward(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_
     bp.in = in;
     bp.gr = gr;
     bp.v2p = ws.v2p;
-    bp.work = ws.work;
-    bp.work_count = ws.work_count;
+    bp.big = ws.big;
+    bp.big_ctr = ws.big_ctr;
     bp.chunk = chunk_voxels(d);
     bp.canon = ws.canon;
     bp.aux = ws.aux;

@@ -43,6 +43,7 @@ struct BwdParams {
 };
 
 __global__ void __launch_bounds__(256) voxel_map_kernel(const BwdParams p) {
+    pdl_launch_dependents();   // the pair kernels may become resident; they wait before using the map
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.big_ctr = 0ull;
     const int H = p.d.H, W = p.d.W, D = p.d.D;
     for (long long n = blockIdx.x * 256ll + threadIdx.x; n < p.d.N; n += 256ll * gridDim.x) {
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(256) voxel_map_kernel(const BwdParams p) {
 //   z = dL/ddensity[n]
 //   w = 1 / probability[n]  if probability[n] > 1e-9 else 0   (0 switches the logits branch off)
 __global__ void __launch_bounds__(256) prob_aux_kernel(const BwdParams p, int C) {
+    pdl_launch_dependents();
     for (long long n = blockIdx.x * 256ll + threadIdx.x; n < p.d.N; n += 256ll * gridDim.x) {
         float x = 0.f;
         for (int k = 0; k < C; ++k) x = fmaf(__ldg(p.gr.logits_grad + n * C + k), __ldg(p.gr.logits + n * C + k), x);
@@ -75,6 +77,9 @@ __global__ void __launch_bounds__(256) prob_aux_kernel(const BwdParams p, int C)
         p.aux[n] = make_float4(x, (1.f - __ldg(p.gr.bin_logits + n)) * __ldg(p.gr.bin_logits_grad + n),
                                __ldg(p.gr.density_grad + n), Z > 1e-9f ? __fdiv_rn(1.f, Z) : 0.f);
     }
+    // runs beside voxel_map_kernel (nothing above depends on it) but must not COMPLETE before it: the pair
+    // kernel's wait only covers the grid launched immediately before it
+    pdl_wait();
 }
 
 // One (Gaussian, point) pair's point-side data, fetched one iteration ahead of its use.
@@ -429,6 +434,8 @@ __global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_sm
     BoxWalk box;
     box.init(lo, hi, empty, p.d.W, p.d.D);
     const bool big = box.vol > kBigBox;
+    pdl_launch_dependents();
+    pdl_wait();   // everything above read the caller's inputs only; the map, the canonical flag and the queue follow
     const bool canon = *p.canon != 0;   // then voxel index == point index and the map need not be read
     if (!big) {
         box.start(lane, box.vol, 32);
@@ -450,6 +457,7 @@ __global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_sm
 template <int C, bool PROB>
 __global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_big_kernel(const BwdParams p) {
     constexpr int kBwdThreads = bwd_threads(PROB);
+    pdl_wait();
     const unsigned long long ctr = *p.big_ctr;
     const int nbig = static_cast<int>(ctr >> 40);
     const long long total = static_cast<long long>(ctr & ((1ull << 40) - 1));
@@ -548,18 +556,21 @@ static int launch_backward_t(const BwdParams &bp, int num_sms, cudaStream_t stre
         GF_CUDA_TRY(cudaMemsetAsync(bp.canon, 0, 4, stream));
     const long long want = (static_cast<long long>(d.N) + 255) / 256;
     const int grid0 = static_cast<int>(want < 16ll * num_sms ? (want > 0 ? want : 1) : 16ll * num_sms);
-    voxel_map_kernel<<<grid0, 256, 0, stream>>>(bp);
+    voxel_map_kernel<<<grid0, 256, 0, stream>>>(bp);   // plain stream order: never overlaps the previous call
     GF_CUDA_TRY(cudaGetLastError());
     if (PROB) {
-        prob_aux_kernel<<<grid0, 256, 0, stream>>>(bp, C);
-        GF_CUDA_TRY(cudaGetLastError());
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid0); cfg.blockDim = dim3(256); cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        GF_CUDA_TRY(cudaLaunchKernelEx(&cfg, prob_aux_kernel, bp, static_cast<int>(C)));
     }
     constexpr int kBwdThreads = bwd_threads(PROB);
     const int per_cta = kBwdThreads / 32;
-    backward_small_kernel<C, PROB><<<(d.G + per_cta - 1) / per_cta, kBwdThreads, 0, stream>>>(bp);
-    GF_CUDA_TRY(cudaGetLastError());
-    backward_big_kernel<C, PROB><<<num_sms * bwd_ctas(PROB) * 2, kBwdThreads, 0, stream>>>(bp);
-    GF_CUDA_TRY(cudaGetLastError());
+    GF_CUDA_TRY(launch_chained(backward_small_kernel<C, PROB>, dim3((d.G + per_cta - 1) / per_cta), dim3(kBwdThreads), 0, stream, bp));
+    GF_CUDA_TRY(launch_chained(backward_big_kernel<C, PROB>, dim3(num_sms * bwd_ctas(PROB) * 2), dim3(kBwdThreads), 0, stream, bp));
     return GF_OK;
 }
 

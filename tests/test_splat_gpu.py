@@ -102,6 +102,50 @@ def test_generic_points_path():
     h.assert_close(out2.cpu().numpy(), ref2["logits"], what="permuted logits")
 
 
+def test_backward_properties_full_size():
+    """BASELINE config 2 at full size, forward and backward tied together without an oracle run:
+    (i) Euler identities -- the output is linear in the opacities and in the class vectors, so
+        <G, out> == <opa, dL/dopa> == <sem, dL/dsem> for any upstream G;
+    (ii) the backward is linear in the upstream gradient;
+    (iii) the covariance gradient lives on the six gathered entries of the 3x3 only;
+    (iv) a finite difference along a random direction of the means matches <dL/dmeans, direction>."""
+    kw, inp, variant = h.splat_case("gs25600_solid", 5, True)
+    m = h.make_module(kw, variant)
+    t = h.to_dev(inp, requires_grad=True)
+    out = m(t["pts"], t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    g1 = torch.randn(out.shape, device="cuda", generator=gen)
+    g2 = torch.randn(out.shape, device="cuda", generator=gen)
+    wrt = [t["means"], t["opa"], t["sem"], t["cov"]]
+    a = torch.autograd.grad(out, wrt, g1, retain_graph=True)
+    b = torch.autograd.grad(out, wrt, g2, retain_graph=True)
+    c = torch.autograd.grad(out, wrt, g1 + 2 * g2, retain_graph=True)
+    inner = float((g1.double() * out.detach().double()).sum())
+    via_opa = float((t["opa"].detach().double() * a[1].double()).sum())
+    via_sem = float((t["sem"].detach().double() * a[2].double()).sum())
+    assert abs(via_opa - inner) <= 1e-4 * abs(inner) + 1e-3, (via_opa, inner)
+    assert abs(via_sem - inner) <= 1e-4 * abs(inner) + 1e-3, (via_sem, inner)
+    for x, y, z, name in zip(a, b, c, ("means", "opa", "sem", "cov")):
+        ref = (x.double() + 2 * y.double()).cpu().numpy()
+        h.assert_close(z.cpu().numpy(), ref, rtol=1e-3, atol=h.grad_tolerance(ref), what=f"linearity of grad {name}")
+    gcov = a[3].reshape(-1, 9)
+    assert float(gcov[:, [3, 6, 7]].abs().max()) == 0.0
+    # directional finite difference in float64-accumulated loss
+    d = torch.randn(t["means"].shape, device="cuda", generator=gen)
+    d[:, -1] = 0                                        # keep the whole-grid "empty" Gaussian put
+    # the integer box follows the mean's voxel: only move means that cannot cross a voxel face (the op is
+    # discontinuous there, like the reference)
+    frac = ((t["means"].detach() - m.pc_min.view(1, 1, 3)) / m.grid_size) % 1.0
+    d = d * ((frac > 0.1) & (frac < 0.9)).all(dim=-1, keepdim=True)
+    eps = 1e-3
+    with torch.no_grad():
+        lp = (m(t["pts"], t["means"] + eps * d, t["opa"], t["sem"], t["scales"], t["cov"]).double() * g1.double()).sum()
+        lm = (m(t["pts"], t["means"] - eps * d, t["opa"], t["sem"], t["scales"], t["cov"]).double() * g1.double()).sum()
+    fd = float((lp - lm) / (2 * eps))
+    an = float((a[0].double() * d.double()).sum())
+    assert abs(fd - an) <= 2e-2 * max(abs(an), abs(fd)) + 1e-2, (fd, an)
+
+
 def test_backward_generic_points_and_unaligned_gradients():
     """Backward paths off the fast lane: points not in voxel order (voxel -> point map), a subset of the grid
     (empty voxels), and upstream gradients whose storage is only 4- or 8-byte aligned (narrow row loads)."""

@@ -120,10 +120,8 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
     // come from the two preparation kernels, which this grid may have been launched ahead of.
     pdl_wait();
     if (stray) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
-    walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, [&](const float4 *r4, uint32_t zb, bool active) {
+    walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, [&](const float4 *r4, const float4 g0, const float4 g1, const float2 g2, uint32_t zb, bool active) {
         if (active) {
-                    const float4 g0 = r4[0], g1 = r4[1];
-                    const float2 g2 = *reinterpret_cast<const float2 *>(r4 + 2);
                     float wv[VOX];
                     if (column) {
                         // My VOX points share x and y (voxel centres of one z column — every shipped config,

@@ -412,6 +412,14 @@ def side_measurements(dev, kw, inp0, resident, desc):
         feat, shape, start = DAF.feature_maps_format([f.to(dev) for f in fms])
         feat = feat.contiguous()
         loc, w = loc.to(dev), w.to(dev)
+        dev_maps = [f.to(dev) for f in fms]
+        out["daf_format_ms"] = timeit(lambda: DAF.feature_maps_format(dev_maps)[0], reps=10)
+
+        def torch_format():      # the reference's route: reshape + cat + permute, then the copy .contiguous() makes
+            bs, cams, ch = dev_maps[0].shape[:3]
+            return torch.cat([m.reshape(bs, cams, ch, -1) for m in dev_maps], dim=-1).permute(0, 1, 3, 2).contiguous()
+        out["ref_format_torch_ms"] = timeit(torch_format, reps=10)
+        del dev_maps
         out["daf_fwd_ms"] = timeit(lambda: DAF.apply(feat, shape, start, loc, w), reps=10)
         out["daf_fwd_alg_gbs"] = 4 * (feat.numel() + loc.numel() + w.numel() + loc.shape[1] * 128) / (out["daf_fwd_ms"] * 1e-3) / 1e9
     except Exception as e:  # side figures must never sink the headline

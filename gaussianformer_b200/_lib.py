@@ -24,7 +24,7 @@ EXPORTS = (
     "gf_abi_version", "gf_last_error", "gf_splat_supported_classes",
     "gf_splat_forward_workspace_bytes", "gf_splat_backward_workspace_bytes",
     "gf_splat_forward", "gf_splat_backward", "gf_splat_read_flags",
-    "gf_daf_forward", "gf_daf_backward", "gf_splat_set_render_events",
+    "gf_daf_forward", "gf_daf_backward", "gf_daf_format", "gf_splat_set_render_events",
 )
 
 
@@ -58,6 +58,14 @@ class DafDesc(Structure):
                 ("num_scale", c_int32), ("num_pts", c_int32), ("num_groups", c_int32)]
 
 
+DAF_MAX_LEVELS = 8
+
+
+class DafFormatDesc(Structure):
+    _fields_ = [("batch_cams", c_int32), ("num_embeds", c_int32), ("num_scale", c_int32),
+                ("hw", c_int32 * DAF_MAX_LEVELS)]
+
+
 class GfError(RuntimeError):
     pass
 
@@ -89,6 +97,7 @@ def lib():
         L.gf_splat_set_render_events.argtypes = [c_void_p, c_void_p]
         L.gf_daf_forward.argtypes = [POINTER(DafDesc)] + [c_void_p] * 7
         L.gf_daf_backward.argtypes = [POINTER(DafDesc)] + [c_void_p] * 10
+        L.gf_daf_format.argtypes = [POINTER(DafFormatDesc), POINTER(c_void_p), c_void_p, c_int, c_void_p]
         if L.gf_abi_version() != 1:
             raise ImportError("libgf_b200.so: ABI version mismatch")
         _lib = L

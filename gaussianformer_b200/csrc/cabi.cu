@@ -40,6 +40,7 @@ extern const int kNumSupportedClasses;
 struct DafParams;
 int launch_daf_forward(const gf_daf_desc &d, const float *feat, const int32_t *shape, const int32_t *start,
                        const float *loc, const float *weights, float *out, int num_sms, cudaStream_t stream);
+int launch_daf_format(const gf_daf_format_desc &d, float *const *maps, float *table, bool inverse, cudaStream_t stream);
 int launch_daf_backward(const gf_daf_desc &d, const float *feat, const int32_t *shape, const int32_t *start,
                         const float *loc, const float *weights, const float *grad_out, float *grad_feat,
                         float *grad_loc, float *grad_weights, int num_sms, cudaStream_t stream);
@@ -233,6 +234,21 @@ int gf_daf_backward(const gf_daf_desc *desc, const float *feat, const int32_t *s
     if (rc != GF_OK) return rc;
     return launch_daf_backward(*desc, feat, shape, start, loc, weights, grad_output, grad_feat, grad_loc,
                                grad_weights, num_sms, static_cast<cudaStream_t>(stream_));
+}
+
+int gf_daf_format(const gf_daf_format_desc *desc, float *const *maps, float *table, int inverse, gf_stream_t stream_) {
+    GF_REQUIRE(desc && maps && table, GF_ERR_INVALID_ARG, "daf format: NULL argument");
+    GF_REQUIRE(desc->num_scale >= 1 && desc->num_scale <= GF_DAF_MAX_LEVELS, GF_ERR_UNSUPPORTED,
+               "daf format: num_scale=%d outside [1,%d]", desc->num_scale, GF_DAF_MAX_LEVELS);
+    GF_REQUIRE(desc->batch_cams >= 0 && desc->num_embeds >= 0, GF_ERR_INVALID_ARG, "daf format: negative size");
+    long long rows = 0;
+    for (int l = 0; l < desc->num_scale; ++l) {
+        GF_REQUIRE(desc->hw[l] >= 0, GF_ERR_INVALID_ARG, "daf format: negative level size");
+        GF_REQUIRE(maps[l] || desc->hw[l] == 0, GF_ERR_INVALID_ARG, "daf format: NULL map pointer");
+        rows += desc->hw[l];
+    }
+    GF_REQUIRE(rows < (1ll << 31), GF_ERR_UNSUPPORTED, "daf format: too many rows");
+    return gf::launch_daf_format(*desc, maps, table, inverse != 0, static_cast<cudaStream_t>(stream_));
 }
 
 }  // extern "C"

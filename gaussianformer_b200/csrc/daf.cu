@@ -365,6 +365,115 @@ int launch_daf(const gf_daf_desc &d, const DafParams &dp, bool backward, int num
     return GF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// feature_maps_format: [B*M, C, hw_l] maps <-> channels-last table [B*M, F, C], one tiled transpose
+// ------------------------------------------------------------------------------------------------
+struct FormatParams {
+    float *maps[GF_DAF_MAX_LEVELS];
+    float *table;
+    int hw[GF_DAF_MAX_LEVELS], start[GF_DAF_MAX_LEVELS], tile0[GF_DAF_MAX_LEVELS + 1];   // rows, first row, first tile of a level
+    int L, C, F;
+};
+
+// 64 (rows of the table) x 64 (channels) tiles through shared memory; both global sides move 16 bytes
+// per thread along their contiguous axis (rows of a map, channels of the table).
+template <bool INVERSE>
+__global__ void __launch_bounds__(256) daf_format_kernel(const FormatParams p) {
+    __shared__ float tile[64][65];
+    int lv = 0;
+    while (lv + 1 < p.L && static_cast<int>(blockIdx.x) >= p.tile0[lv + 1]) ++lv;
+    const int r0 = (blockIdx.x - p.tile0[lv]) * 64, c0 = blockIdx.y * 64;
+    const int hw = p.hw[lv];
+    const size_t bm = blockIdx.z;
+    float *map = p.maps[lv] + bm * p.C * hw;                                // [C][hw]
+    float *tab = p.table + (bm * p.F + p.start[lv]) * p.C;                  // [hw][C]
+    const int t = threadIdx.x;
+    const bool vec_rows = (hw & 3) == 0 && (reinterpret_cast<uintptr_t>(map) & 15) == 0;
+    const bool vec_ch = (p.C & 3) == 0 && (reinterpret_cast<uintptr_t>(tab) & 15) == 0;
+    if (!INVERSE) {
+        // map -> tile[row][channel]
+        for (int i = t; i < 64 * 16; i += 256) {
+            const int c = i >> 4, r4 = (i & 15) * 4;
+            if (c0 + c >= p.C) continue;
+            const float *src = map + static_cast<size_t>(c0 + c) * hw + r0 + r4;
+            if (vec_rows && r0 + r4 + 3 < hw) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src));
+                tile[r4][c] = v.x; tile[r4 + 1][c] = v.y; tile[r4 + 2][c] = v.z; tile[r4 + 3][c] = v.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (r0 + r4 + k < hw) tile[r4 + k][c] = __ldg(src + k);
+            }
+        }
+        __syncthreads();
+        for (int i = t; i < 64 * 16; i += 256) {
+            const int r = i >> 4, c4 = (i & 15) * 4;
+            if (r0 + r >= hw || c0 + c4 >= p.C) continue;
+            float *dst = tab + static_cast<size_t>(r0 + r) * p.C + c0 + c4;
+            if (vec_ch && c0 + c4 + 3 < p.C) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(tile[r][c4], tile[r][c4 + 1], tile[r][c4 + 2], tile[r][c4 + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c0 + c4 + k < p.C) dst[k] = tile[r][c4 + k];
+            }
+        }
+    } else {
+        // table -> tile[row][channel] -> map
+        for (int i = t; i < 64 * 16; i += 256) {
+            const int r = i >> 4, c4 = (i & 15) * 4;
+            if (r0 + r >= hw || c0 + c4 >= p.C) continue;
+            const float *src = tab + static_cast<size_t>(r0 + r) * p.C + c0 + c4;
+            if (vec_ch && c0 + c4 + 3 < p.C) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src));
+                tile[r][c4] = v.x; tile[r][c4 + 1] = v.y; tile[r][c4 + 2] = v.z; tile[r][c4 + 3] = v.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c0 + c4 + k < p.C) tile[r][c4 + k] = __ldg(src + k);
+            }
+        }
+        __syncthreads();
+        for (int i = t; i < 64 * 16; i += 256) {
+            const int c = i >> 4, r4 = (i & 15) * 4;
+            if (c0 + c >= p.C) continue;
+            float *dst = map + static_cast<size_t>(c0 + c) * hw + r0 + r4;
+            if (vec_rows && r0 + r4 + 3 < hw) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(tile[r4][c], tile[r4 + 1][c], tile[r4 + 2][c], tile[r4 + 3][c]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (r0 + r4 + k < hw) dst[k] = tile[r4 + k][c];
+            }
+        }
+    }
+}
+
+int launch_daf_format(const gf_daf_format_desc &d, float *const *maps, float *table, bool inverse, cudaStream_t stream) {
+    FormatParams fp{};
+    fp.L = d.num_scale;
+    fp.C = d.num_embeds;
+    fp.table = table;
+    int rows = 0, tiles = 0;
+    for (int l = 0; l < d.num_scale; ++l) {
+        fp.maps[l] = maps[l];
+        fp.hw[l] = d.hw[l];
+        fp.start[l] = rows;
+        fp.tile0[l] = tiles;
+        rows += d.hw[l];
+        tiles += (d.hw[l] + 63) / 64;
+    }
+    fp.tile0[d.num_scale] = tiles;
+    fp.F = rows;
+    if (tiles == 0 || d.batch_cams == 0 || d.num_embeds == 0) return GF_OK;
+    const dim3 grid(tiles, (d.num_embeds + 63) / 64, d.batch_cams);
+    GF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, GF_ERR_UNSUPPORTED, "daf format: too many channels or cameras");
+    if (inverse) daf_format_kernel<true><<<grid, 256, 0, stream>>>(fp);
+    else daf_format_kernel<false><<<grid, 256, 0, stream>>>(fp);
+    GF_CUDA_TRY(cudaGetLastError());
+    return GF_OK;
+}
+
 int launch_daf_forward(const gf_daf_desc &d, const float *feat, const int32_t *shape, const int32_t *start,
                        const float *loc, const float *weights, float *out, int num_sms, cudaStream_t stream) {
     DafParams dp{};

@@ -129,6 +129,19 @@ typedef struct gf_daf_desc {
     int32_t num_groups; /* Gr, divides C */
 } gf_daf_desc;
 
+#define GF_DAF_MAX_LEVELS 8
+
+/* feature_maps_format (ops/deformable_aggregation.py:78-117, forward direction): L maps
+ * [B*M, C, h_l, w_l] (contiguous) <-> one channels-last table [B*M, F, C], F = sum_l h_l*w_l,
+ * level l occupying rows [sum_{k<l} h_k*w_k, ...).  The reference builds it with reshape + cat +
+ * permute and leaves the transposing copy to every later .contiguous(). */
+typedef struct gf_daf_format_desc {
+    int32_t batch_cams; /* B*M */
+    int32_t num_embeds; /* C */
+    int32_t num_scale;  /* L <= GF_DAF_MAX_LEVELS */
+    int32_t hw[GF_DAF_MAX_LEVELS]; /* h_l*w_l */
+} gf_daf_format_desc;
+
 int gf_abi_version(void);
 const char *gf_last_error(void);
 
@@ -169,6 +182,12 @@ int gf_daf_backward(const gf_daf_desc *desc, const float *mc_ms_feat, const int3
                     const int32_t *scale_start_index, const float *sample_location,
                     const float *weights, const float *grad_output, float *grad_mc_ms_feat,
                     float *grad_sampling_location, float *grad_weights, gf_stream_t stream);
+
+/* One pass over the data in either direction: inverse == 0 gathers the L maps into `table`
+ * (fully overwritten); inverse != 0 scatters `table` back into the L maps (fully overwritten; this is the
+ * gradient of the forward direction).  maps[l] are device pointers, the array itself lives on the host. */
+int gf_daf_format(const gf_daf_format_desc *desc, float *const *maps, float *table, int inverse,
+                  gf_stream_t stream);
 
 #ifdef __cplusplus
 }

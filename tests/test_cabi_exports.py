@@ -33,7 +33,8 @@ def test_struct_layouts_follow_the_header():
     src = open(os.path.join(ROOT, "include", "gf_b200.h")).read()
     for cname, cls in (("gf_splat_desc", _lib.SplatDesc), ("gf_splat_inputs", _lib.SplatInputs),
                        ("gf_splat_outputs", _lib.SplatOutputs), ("gf_splat_grads", _lib.SplatGrads),
-                       ("gf_daf_desc", _lib.DafDesc)):
+                       ("gf_daf_desc", _lib.DafDesc),
+                       ("gf_daf_format_desc", _lib.DafFormatDesc)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []

@@ -76,3 +76,28 @@ def test_daf_full_size_properties():
     ref = oracle.daf_forward(feat.detach().cpu().numpy(), shape.cpu().numpy(), start.cpu().numpy(),
                              loc[:, sel].contiguous().numpy(), w[:, sel].contiguous().numpy(), "f64")
     h.assert_close(out.detach()[:, sel.cuda()].cpu().numpy(), ref, what="daf sampled subset")
+
+
+@pytest.mark.parametrize("channels,levels", [
+    (128, ((108, 200), (54, 100), (27, 50), (14, 25))),    # BASELINE config-2 maps (1 sample x 6 cameras)
+    (24, ((5, 7), (3, 3), (1, 1))),                         # ragged: nothing divides the tile or vector sizes
+    (130, ((9, 13),)),
+])
+def test_feature_maps_format_is_the_reference_layout(channels, levels):
+    """The fused table kernel is a pure data movement: bit-exact against the reference's
+    reshape + cat + permute (ops/deformable_aggregation.py:78-95), and its gradient is the inverse
+    scatter (what autograd derives for the reference's view ops)."""
+    gen = torch.Generator().manual_seed(5)
+    bs, cams = (1, 6) if channels == 128 else (2, 3)
+    maps = [torch.randn(bs, cams, channels, h_, w_, generator=gen).cuda().requires_grad_(True) for h_, w_ in levels]
+    col, shape, start = DAF.feature_maps_format(maps)
+    assert col.is_contiguous() and col.shape == (bs, cams, sum(h_ * w_ for h_, w_ in levels), channels)
+    ref_col = torch.cat([m.detach().reshape(bs, cams, channels, -1) for m in maps], dim=-1).permute(0, 1, 3, 2)
+    assert torch.equal(col.detach(), ref_col)
+    assert shape.tolist() == [list(l) for l in levels]
+    assert start.tolist() == [int(s) for s in np.cumsum([0] + [h_ * w_ for h_, w_ in levels])[:-1]]
+    g = torch.randn(col.shape, generator=gen).cuda()
+    col.backward(g)
+    back = DAF.feature_maps_format([g, shape, start], inverse=True)      # the reference's inverse: views of g
+    for m, b in zip(maps, back):
+        assert torch.equal(m.grad, b.contiguous())

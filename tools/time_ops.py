@@ -31,6 +31,14 @@ print("prob bwd ms", timeit(lambda: torch.autograd.grad([lg, bl, de], [tp["means
 fms, loc, w = make_daf_inputs(seed=0)
 feat, shape, start = DAF.feature_maps_format([f.to(dev) for f in fms])
 feat = feat.contiguous().requires_grad_(); loc = loc.to(dev).requires_grad_(); w = w.to(dev).requires_grad_()
+dev_maps = [f.to(dev) for f in fms]
+print("format fused ms", timeit(lambda: DAF.feature_maps_format(dev_maps)[0]))
+from gaussianformer_b200.ops.deformable_aggregation import _FeatureMapsToTable
+print("format kernel via autograd.Function only ms", timeit(lambda: _FeatureMapsToTable.apply(*dev_maps)))
+def torch_format():
+    bs, cams, ch = dev_maps[0].shape[:3]
+    return torch.cat([m.reshape(bs, cams, ch, -1) for m in dev_maps], dim=-1).permute(0, 1, 3, 2).contiguous()
+print("format reference route (cat + permute + contiguous) ms", timeit(torch_format))
 print("daf fwd ms", timeit(lambda: DAF.apply(feat, shape, start, loc, w)))
 o = DAF.apply(feat, shape, start, loc, w); go = torch.randn_like(o)
 print("daf bwd ms (incl. 3 zero fills)", timeit(lambda: torch.autograd.grad(o, [feat, loc, w], go, retain_graph=True), reps=5))

@@ -15,7 +15,10 @@ namespace gf {
 #endif
 constexpr int kQuadSeg = 512;   // list entries resolved per segment
 constexpr int kBatch = 32;      // records staged per ring slot
-constexpr int kRing = 4;        // ring slots: a warp may run up to kRing-2 batches ahead of the slowest one
+#ifndef GF_TILE_RING
+#define GF_TILE_RING 5   // measured: 5, 6, 7 slots 72.0 us per step, 4 and 8 slots 73.4 us
+#endif
+constexpr int kRing = GF_TILE_RING;   // ring slots: a warp may run up to kRing-2 batches ahead of the slowest one
 
 template <int C, int VOX>
 struct RenderSmem {

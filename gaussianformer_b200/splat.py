@@ -219,6 +219,11 @@ class _LocalAggregatorBase(nn.Module):
             self.__dict__["_cfg_cache"] = cfg
         return cfg
 
+    def forward_from_srt(self, pts, means3D, opacities, semantics, scales, rotations):
+        """Entry point next to the reference signature: takes the Gaussians' scales and
+        rotation quaternions instead of a precomputed inverse covariance and never leaves the device."""
+        return self.forward(pts, means3D, opacities, semantics, scales, inverse_covariance_from_srt(scales, rotations))
+
     def _run(self, pts, means3D, opacities, semantics, scales, cov3D):
         _require_cuda(pts, means3D, opacities, semantics, scales, cov3D)
         assert not pts.requires_grad
@@ -229,6 +234,24 @@ class _LocalAggregatorBase(nn.Module):
             outs.append(_SplatFunction.apply(pts[b], means3D[b], opacities[b], semantics[b],
                                              scales[b].detach(), cov3D[b], cfg))
         return outs
+
+
+def inverse_covariance_from_srt(scales, rotations):
+    """Sigma^-1 = R^T diag(1/s^2) R on the device, differentiable.
+
+    ``GaussianHead.prepare_gaussian_args`` (model/head/gaussian_head.py:111-119) builds ``Cov = (S R)^T (S R)``
+    and inverts it numerically on the CPU (``Cov.cpu().inverse().cuda()``, a blocking round trip per
+    supervised layer).  ``R`` is a rotation, so the inverse is available in closed form; the quaternion ->
+    matrix map is the reference's (model/utils/utils.py:20-66, (w, x, y, z), normalised first)."""
+    q = torch.nn.functional.normalize(rotations, dim=-1)
+    w, x, y, z = q.unbind(-1)
+    R = torch.stack([
+        torch.stack([w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)], -1),
+        torch.stack([2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)], -1),
+        torch.stack([2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z], -1),
+    ], dim=-2)
+    inv_s2 = 1.0 / (scales * scales)
+    return torch.matmul(R.transpose(-1, -2) * inv_s2.unsqueeze(-2), R)
 
 
 class LocalAggregator(_LocalAggregatorBase):

@@ -290,3 +290,28 @@ def test_other_class_counts(C, variant):
     gm, go, gs, gc = h.oracle_backward(kw, inp, variant, tuple(x.numpy() for x in g), saved)
     h.assert_close(t["sem"].grad[0].cpu().numpy(), gs, rtol=2e-3, atol=5 * h.grad_tolerance(gs), what=f"C={C} grad sem")
     h.assert_close(t["means"].grad[0].cpu().numpy(), gm, rtol=2e-3, atol=5 * h.grad_tolerance(gm), what=f"C={C} grad means")
+
+
+def test_forward_from_scales_and_rotations():
+    """The closed-form device-side Sigma^-1 (forward_from_srt) against the reference's route
+    (Cov = (S R)^T (S R), numerical inverse on the CPU): same logits, and gradients reach scales/rotations."""
+    from gaussianformer_b200.splat import inverse_covariance_from_srt
+    from gaussianformer_b200.synthetic import inverse_covariance
+    kw, inp, variant = h.splat_case("tiny", 13, True)
+    gen = torch.Generator().manual_seed(2)
+    G = inp["means"].shape[1]
+    rots = torch.randn(1, G, 4, generator=gen)
+    scales = inp["scales"]
+    ref_cov = inverse_covariance(scales, rots)                       # CPU inverse, like the reference
+    dev_cov = inverse_covariance_from_srt(scales.cuda(), rots.cuda())
+    h.assert_close(dev_cov.cpu().numpy(), ref_cov.numpy(), rtol=1e-4, atol=1e-4 * float(ref_cov.abs().max()), what="Sigma^-1")
+    m = h.make_module(kw, variant)
+    t = h.to_dev(dict(inp, cov=ref_cov))
+    out_ref = m(t["pts"], t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
+    s_d = scales.cuda().requires_grad_(True)
+    r_d = rots.cuda().requires_grad_(True)
+    out = m.forward_from_srt(t["pts"], t["means"], t["opa"], t["sem"], s_d, r_d)
+    h.assert_close(out.detach().cpu().numpy(), out_ref.cpu().numpy(), rtol=1e-3, atol=1e-4, what="logits from s, r")
+    out.sum().backward()
+    assert s_d.grad is not None and r_d.grad is not None
+    assert torch.isfinite(s_d.grad).all() and torch.isfinite(r_d.grad).all() and float(r_d.grad.abs().max()) > 0

@@ -425,6 +425,29 @@ def side_measurements(dev, kw, inp0, resident, desc):
     except Exception as e:  # side figures must never sink the headline
         out["extras_error"] = repr(e)
     try:
+        # fused caller path: masked softmax + op + key-point sum, against the same three steps done
+        # the reference's way (PyTorch softmax -> our drop-in op -> .sum) on the same inputs
+        from gaussianformer_b200.ops import deformable_aggregation_fused
+        from gaussianformer_b200.synthetic import make_daf_fused_inputs, reference_fused_composition
+        fms, loc, lg, pm, _ = make_daf_fused_inputs(seed=0)
+        feat, shape, start = DAF.feature_maps_format([f.to(dev) for f in fms])
+        feat = feat.contiguous()
+        loc, lg, pm = loc.to(dev), lg.to(dev), pm.to(dev)
+        with torch.no_grad():
+            out["daf_fused_fwd_ms"] = timeit(lambda: deformable_aggregation_fused(feat, shape, start, loc, lg, pm), reps=10)
+            out["daf_unfused_fwd_ms"] = timeit(lambda: reference_fused_composition(DAF.apply, feat, shape, start, loc, lg, pm), reps=10)
+        feat.requires_grad_(True); loc.requires_grad_(True); lg.requires_grad_(True)
+        g = torch.randn(1, lg.shape[1], feat.shape[-1], device=dev)
+
+        def fwd_bwd(fn):
+            o = fn(feat, shape, start, loc, lg, pm)
+            return torch.autograd.grad(o, [feat, loc, lg], g)
+        out["daf_fused_fwd_bwd_ms"] = timeit(lambda: fwd_bwd(deformable_aggregation_fused), reps=5)
+        out["daf_unfused_fwd_bwd_ms"] = timeit(lambda: fwd_bwd(lambda *a: reference_fused_composition(DAF.apply, *a)), reps=5)
+        del feat, loc, lg, pm, g
+    except Exception as e:
+        out["daf_fused_error"] = repr(e)
+    try:
         from oracle import build_ref
         if build_ref.available("gf_ref_daf"):
             mod = build_ref.load_ref("gf_ref_daf")

@@ -25,6 +25,7 @@ EXPORTS = (
     "gf_splat_forward_workspace_bytes", "gf_splat_backward_workspace_bytes",
     "gf_splat_forward", "gf_splat_backward", "gf_splat_read_flags",
     "gf_daf_forward", "gf_daf_backward", "gf_daf_format", "gf_splat_set_render_events",
+    "gf_daf_fused_supported", "gf_daf_fused_forward", "gf_daf_fused_backward",
 )
 
 
@@ -56,6 +57,10 @@ class SplatGrads(Structure):
 class DafDesc(Structure):
     _fields_ = [("batch", c_int32), ("num_cams", c_int32), ("num_feat", c_int32), ("num_embeds", c_int32),
                 ("num_scale", c_int32), ("num_pts", c_int32), ("num_groups", c_int32)]
+
+
+class DafFusedDesc(Structure):
+    _fields_ = [("d", DafDesc), ("pts_per_anchor", c_int32)]
 
 
 DAF_MAX_LEVELS = 8
@@ -97,6 +102,9 @@ def lib():
         L.gf_splat_set_render_events.argtypes = [c_void_p, c_void_p]
         L.gf_daf_forward.argtypes = [POINTER(DafDesc)] + [c_void_p] * 7
         L.gf_daf_backward.argtypes = [POINTER(DafDesc)] + [c_void_p] * 10
+        L.gf_daf_fused_supported.argtypes = [POINTER(DafFusedDesc)]
+        L.gf_daf_fused_forward.argtypes = [POINTER(DafFusedDesc)] + [c_void_p] * 10
+        L.gf_daf_fused_backward.argtypes = [POINTER(DafFusedDesc)] + [c_void_p] * 14
         L.gf_daf_format.argtypes = [POINTER(DafFormatDesc), POINTER(c_void_p), c_void_p, c_int, c_void_p]
         if L.gf_abi_version() != 1:
             raise ImportError("libgf_b200.so: ABI version mismatch")

@@ -45,6 +45,15 @@ int launch_daf_backward(const gf_daf_desc &d, const float *feat, const int32_t *
                         const float *loc, const float *weights, const float *grad_out, float *grad_feat,
                         float *grad_loc, float *grad_weights, int num_sms, cudaStream_t stream);
 
+bool daf_fused_supported(const gf_daf_desc &d, int K);
+int launch_daf_fused_forward(const gf_daf_desc &d, int K, const float *feat, const int32_t *shape, const int32_t *start,
+                             const float *loc, const float *logits, const uint8_t *pmask, const uint8_t *wmask,
+                             float *out, float *stats, int num_sms, cudaStream_t stream);
+int launch_daf_fused_backward(const gf_daf_desc &d, int K, const float *feat, const int32_t *shape, const int32_t *start,
+                              const float *loc, const float *logits, const uint8_t *pmask, const uint8_t *wmask,
+                              const float *stats, const float *out, const float *grad_out, float *grad_feat,
+                              float *grad_loc, float *grad_logits, int num_sms, cudaStream_t stream);
+
 thread_local cudaEvent_t g_ev_before = nullptr, g_ev_after = nullptr;
 
 bool pdl_enabled() {
@@ -234,6 +243,57 @@ int gf_daf_backward(const gf_daf_desc *desc, const float *feat, const int32_t *s
     if (rc != GF_OK) return rc;
     return launch_daf_backward(*desc, feat, shape, start, loc, weights, grad_output, grad_feat, grad_loc,
                                grad_weights, num_sms, static_cast<cudaStream_t>(stream_));
+}
+
+static int check_daf_fused(const gf_daf_fused_desc *fd) {
+    GF_REQUIRE(fd != nullptr, GF_ERR_INVALID_ARG, "daf fused: desc is NULL");
+    int rc = check_daf(&fd->d);
+    if (rc != GF_OK) return rc;
+    GF_REQUIRE(fd->pts_per_anchor >= 1, GF_ERR_INVALID_ARG, "daf fused: pts_per_anchor < 1");
+    GF_REQUIRE(fd->d.num_pts % fd->pts_per_anchor == 0, GF_ERR_INVALID_ARG,
+               "daf fused: num_pts=%d is not a multiple of pts_per_anchor=%d", fd->d.num_pts, fd->pts_per_anchor);
+    GF_REQUIRE(daf_fused_supported(fd->d, fd->pts_per_anchor), GF_ERR_UNSUPPORTED,
+               "daf fused: shape not supported by the fused kernel (C=%d, groups=%d, cams*levels=%d); use gf_daf_forward",
+               fd->d.num_embeds, fd->d.num_groups, fd->d.num_cams * fd->d.num_scale);
+    return GF_OK;
+}
+
+int gf_daf_fused_supported(const gf_daf_fused_desc *fd) {
+    if (fd == nullptr || check_daf(&fd->d) != GF_OK || fd->pts_per_anchor < 1) return 0;
+    return daf_fused_supported(fd->d, fd->pts_per_anchor) ? 1 : 0;
+}
+
+int gf_daf_fused_forward(const gf_daf_fused_desc *fd, const float *feat, const int32_t *shape, const int32_t *start,
+                         const float *loc, const float *logits, const uint8_t *point_mask, const uint8_t *weight_mask,
+                         float *output, float *stats, gf_stream_t stream_) {
+    int rc = check_daf_fused(fd);
+    if (rc != GF_OK) return rc;
+    if (static_cast<long long>(fd->d.batch) * fd->d.num_pts == 0) return GF_OK;
+    GF_REQUIRE(feat && shape && start && loc && logits && output && stats, GF_ERR_INVALID_ARG,
+               "daf fused forward: NULL pointer");
+    int num_sms = 1;
+    rc = num_sms_of_current_device(&num_sms);
+    if (rc != GF_OK) return rc;
+    return launch_daf_fused_forward(fd->d, fd->pts_per_anchor, feat, shape, start, loc, logits, point_mask, weight_mask,
+                                    output, stats, num_sms, static_cast<cudaStream_t>(stream_));
+}
+
+int gf_daf_fused_backward(const gf_daf_fused_desc *fd, const float *feat, const int32_t *shape, const int32_t *start,
+                          const float *loc, const float *logits, const uint8_t *point_mask, const uint8_t *weight_mask,
+                          const float *stats, const float *output, const float *grad_output, float *grad_feat,
+                          float *grad_loc, float *grad_logits, gf_stream_t stream_) {
+    int rc = check_daf_fused(fd);
+    if (rc != GF_OK) return rc;
+    if (static_cast<long long>(fd->d.batch) * fd->d.num_pts == 0) return GF_OK;
+    GF_REQUIRE(feat && shape && start && loc && logits && stats && output && grad_output && grad_feat && grad_loc &&
+                   grad_logits,
+               GF_ERR_INVALID_ARG, "daf fused backward: NULL pointer");
+    int num_sms = 1;
+    rc = num_sms_of_current_device(&num_sms);
+    if (rc != GF_OK) return rc;
+    return launch_daf_fused_backward(fd->d, fd->pts_per_anchor, feat, shape, start, loc, logits, point_mask, weight_mask,
+                                     stats, output, grad_output, grad_feat, grad_loc, grad_logits, num_sms,
+                                     static_cast<cudaStream_t>(stream_));
 }
 
 int gf_daf_format(const gf_daf_format_desc *desc, float *const *maps, float *table, int inverse, gf_stream_t stream_) {

@@ -10,12 +10,9 @@
 //   * backward: feature gradients go out as 16-byte vector atomics (one per lane per corner),
 //     weight gradients are reduced over the lanes of a group with shuffles and written by one
 //     lane, location gradients are reduced over the warp — no scalar atomic storms.
-#include "common.cuh"
+#include "daf_pair.cuh"
 
 namespace gf {
-
-constexpr int kDafThreads = 256;
-constexpr int kMaxLevels = 8;
 
 struct DafParams {
     gf_daf_desc d;
@@ -190,45 +187,6 @@ __global__ void __launch_bounds__(kDafThreads) daf_kernel(const DafParams p) {
 //   every visit       : 2-3 uniform LDS.128 for the setup, one weight load, 4 coalesced 16-byte row
 //                       loads per lane, 16 FMAs
 // ------------------------------------------------------------------------------------------------
-struct PairSetup {     // 64 bytes per (camera, level) pair
-    int row[4];        // element offset of each corner row inside the batch's feature block (row * C)
-    float w[4];        // bilinear corner weights, 0 where the corner is outside the map
-    float lh, lw;      // fractional parts (backward only)
-    float fh, fw;      // level height / width as floats (backward only)
-    int ok;            // bit k: corner k lies inside the map
-    int cam;           // camera of this pair
-    int pad0, pad1;
-};
-
-__device__ __forceinline__ bool pair_setup(const DafParams &p, const int *lh, const int *lw, const int *ls,
-                                           long long bp, int m, int lv, PairSetup &o) {
-    const int M = p.d.num_cams, F = p.d.num_feat, C = p.d.num_embeds;
-    const float lx = __ldg(p.loc + (bp * M + m) * 2), ly = __ldg(p.loc + (bp * M + m) * 2 + 1);
-    const bool gate = lx > 0.f && lx < 1.f && ly > 0.f && ly < 1.f;
-    const int h = lh[lv], w = lw[lv];
-    const float y_im = ly * static_cast<float>(h) - 0.5f, x_im = lx * static_cast<float>(w) - 0.5f;
-    const float yf = floorf(y_im), xf = floorf(x_im);
-    const int y0 = static_cast<int>(yf), x0 = static_cast<int>(xf);
-    o.lh = y_im - yf; o.lw = x_im - xf;
-    o.fh = static_cast<float>(h); o.fw = static_cast<float>(w);
-    const float hh = 1.f - o.lh, hw = 1.f - o.lw;
-    const bool oky0 = y0 >= 0, oky1 = y0 + 1 <= h - 1, okx0 = x0 >= 0, okx1 = x0 + 1 <= w - 1;
-    const int cy0 = max(y0, 0), cy1 = min(y0 + 1, h - 1), cx0 = max(x0, 0), cx1 = min(x0 + 1, w - 1);
-    const int base = m * F + ls[lv];
-    o.row[0] = (base + cy0 * w + cx0) * C;
-    o.row[1] = (base + cy0 * w + cx1) * C;
-    o.row[2] = (base + cy1 * w + cx0) * C;
-    o.row[3] = (base + cy1 * w + cx1) * C;
-    o.w[0] = (oky0 && okx0) ? hh * hw : 0.f;
-    o.w[1] = (oky0 && okx1) ? hh * o.lw : 0.f;
-    o.w[2] = (oky1 && okx0) ? o.lh * hw : 0.f;
-    o.w[3] = (oky1 && okx1) ? o.lh * o.lw : 0.f;
-    o.ok = (oky0 && okx0 ? 1 : 0) | (oky0 && okx1 ? 2 : 0) | (oky1 && okx0 ? 4 : 0) | (oky1 && okx1 ? 8 : 0);
-    o.cam = m;
-    o.pad0 = o.pad1 = 0;
-    return gate;
-}
-
 template <bool BACKWARD>
 __global__ void __launch_bounds__(kDafThreads, BACKWARD ? 3 : 4) daf_fast_kernel(const DafParams p) {
     __shared__ int lh[kMaxLevels], lw[kMaxLevels], ls[kMaxLevels];
@@ -254,7 +212,7 @@ __global__ void __launch_bounds__(kDafThreads, BACKWARD ? 3 : 4) daf_fast_kernel
         bool gate = false;
         if (lane < npair) {
             PairSetup ps;
-            gate = pair_setup(p, lh, lw, ls, bp, my_cam, my_lv, ps);
+            gate = pair_setup(p.d, p.loc, lh, lw, ls, bp, my_cam, my_lv, ps);
             mine[lane] = ps;
         }
         const uint32_t visible = __ballot_sync(0xffffffffu, gate);
@@ -336,16 +294,6 @@ __global__ void __launch_bounds__(kDafThreads, BACKWARD ? 3 : 4) daf_fast_kernel
     }
 }
 
-static bool vec4_ok(const gf_daf_desc &d) {
-    if (d.num_embeds % 128 != 0) return false;
-    if (d.num_cams * d.num_scale > 32) return false;
-    if (static_cast<long long>(d.num_cams) * d.num_feat * d.num_embeds >= (1ll << 31)) return false;  // int32 row offsets
-    const int gdim = d.num_embeds / d.num_groups;
-    if (gdim % 4 != 0) return false;
-    const int lpg = gdim / 4;
-    return lpg <= 32 && (lpg & (lpg - 1)) == 0;
-}
-
 int launch_daf(const gf_daf_desc &d, const DafParams &dp, bool backward, int num_sms, cudaStream_t stream) {
     const long long npts = static_cast<long long>(d.batch) * d.num_pts;
     if (npts == 0) return GF_OK;
@@ -353,7 +301,7 @@ int launch_daf(const gf_daf_desc &d, const DafParams &dp, bool backward, int num
     long long want = (npts + per_cta - 1) / per_cta;
     const long long cap = static_cast<long long>(num_sms) * 64;
     const int grid = static_cast<int>(want < cap ? want : cap);
-    const bool v4 = vec4_ok(d);
+    const bool v4 = daf_vec4_ok(d);
     if (backward) {
         if (v4) daf_fast_kernel<true><<<grid, kDafThreads, 0, stream>>>(dp);
         else daf_kernel<1, true><<<grid, kDafThreads, 0, stream>>>(dp);

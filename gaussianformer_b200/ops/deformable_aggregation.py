@@ -4,6 +4,10 @@
 sampling_location, weights)`` and the static ``feature_maps_format`` keep the reference's
 signatures and dtype normalisation (``.float()`` / ``.int()``); the kernels are the sm_100a ones
 behind ``gf_daf_forward`` / ``gf_daf_backward`` (``include/gf_b200.h``).
+
+``deformable_aggregation_fused`` is an opt-in entry point next to it: the op together
+with the masked joint softmax of its weights and the sum over the key points that
+``DeformableFeatureAggregation.forward`` wraps around it (``deformable_module.py:213-228,242``).
 """
 from __future__ import annotations
 
@@ -13,7 +17,7 @@ import torch
 from torch.autograd.function import Function, once_differentiable
 
 from .. import _lib
-from .._lib import DAF_MAX_LEVELS, DafDesc, DafFormatDesc
+from .._lib import DAF_MAX_LEVELS, DafDesc, DafFormatDesc, DafFusedDesc
 
 
 def _ptr(t):
@@ -156,3 +160,92 @@ class DeformableAggregationFunction(Function):
         return grad_feat, None, None, grad_loc, grad_w
 
     feature_maps_format = staticmethod(feature_maps_format)
+
+
+class DeformableAggregationFusedFunction(Function):
+    """``[B, A, C] = sum_k DAF(feat, loc, masked_softmax(weight_logits))[b, a*K + k]`` in one kernel
+    (``gf_daf_fused_forward`` / ``gf_daf_fused_backward``).  Gradients: ``mc_ms_feat``,
+    ``sampling_location``, ``weight_logits``."""
+
+    @staticmethod
+    def forward(ctx, mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weight_logits,
+                point_mask=None, weight_mask=None):
+        if weight_logits.dim() != 6:
+            raise ValueError("weight_logits must be [B, A, K, M, L, Gr] (deformable_module.py:177-189)")
+        B, A, K, M, L, Gr = weight_logits.shape
+        mc_ms_feat, spatial_shape, scale_start_index, sampling_location, logits = _normalise(
+            mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weight_logits)
+        if sampling_location.shape != (B, A * K, M, 2):
+            raise ValueError(f"sampling_location must be [B, A*K, M, 2] = {(B, A * K, M, 2)}, got {tuple(sampling_location.shape)}")
+        masks = []
+        for name, mk, shape in (("point_mask", point_mask, (B, A, K, M)), ("weight_mask", weight_mask, (B, A, K, M, L, Gr))):
+            if mk is not None:
+                if not mk.is_cuda or tuple(mk.shape) != shape:
+                    raise ValueError(f"{name} must be a CUDA tensor of shape {shape}")
+                mk = (mk if mk.dtype in (torch.bool, torch.uint8) else mk != 0).contiguous()
+            masks.append(mk)
+        point_mask, weight_mask = masks
+        fd = DafFusedDesc()
+        fd.d = _desc(mc_ms_feat, spatial_shape, sampling_location, logits.view(B, A * K, M, L, Gr))
+        fd.pts_per_anchor = K
+        dev = mc_ms_feat.device
+        with torch.cuda.device(dev):
+            output = torch.empty((B, A, fd.d.num_embeds), dtype=torch.float32, device=dev)
+            stats = torch.empty((B, A, Gr, 2), dtype=torch.float32, device=dev)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(_lib.lib().gf_daf_fused_forward(
+                ctypes.byref(fd), _ptr(mc_ms_feat), _ptr(spatial_shape), _ptr(scale_start_index), _ptr(sampling_location),
+                _ptr(logits), _ptr(point_mask) if point_mask is not None else None,
+                _ptr(weight_mask) if weight_mask is not None else None, _ptr(output), _ptr(stats), stream))
+        ctx.fd = fd
+        ctx.has_masks = (point_mask is not None, weight_mask is not None)
+        saved = [mc_ms_feat, spatial_shape, scale_start_index, sampling_location, logits, stats, output]
+        saved += [m for m in (point_mask, weight_mask) if m is not None]
+        ctx.save_for_backward(*saved)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        saved = list(ctx.saved_tensors)
+        mc_ms_feat, spatial_shape, scale_start_index, sampling_location, logits, stats, output = saved[:7]
+        rest = saved[7:]
+        point_mask = rest.pop(0) if ctx.has_masks[0] else None
+        weight_mask = rest.pop(0) if ctx.has_masks[1] else None
+        dev = mc_ms_feat.device
+        grad_output = grad_output.contiguous().float()
+        with torch.cuda.device(dev):
+            grad_feat = torch.zeros_like(mc_ms_feat)
+            grad_loc = torch.zeros_like(sampling_location)
+            grad_logits = torch.empty_like(logits)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(_lib.lib().gf_daf_fused_backward(
+                ctypes.byref(ctx.fd), _ptr(mc_ms_feat), _ptr(spatial_shape), _ptr(scale_start_index),
+                _ptr(sampling_location), _ptr(logits), _ptr(point_mask) if point_mask is not None else None,
+                _ptr(weight_mask) if weight_mask is not None else None, _ptr(stats), _ptr(output), _ptr(grad_output),
+                _ptr(grad_feat), _ptr(grad_loc), _ptr(grad_logits), stream))
+        return grad_feat, None, None, grad_loc, grad_logits, None, None
+
+
+def fused_supported(num_embeds, num_groups, num_cams, num_levels, num_feat=1, num_pts=1):
+    """True when ``deformable_aggregation_fused`` has a kernel for this shape (otherwise compose
+    ``DeformableAggregationFunction`` with the PyTorch softmax as the reference does)."""
+    fd = DafFusedDesc()
+    fd.d.batch, fd.d.num_cams, fd.d.num_feat, fd.d.num_embeds = 1, num_cams, num_feat, num_embeds
+    fd.d.num_scale, fd.d.num_pts, fd.d.num_groups = num_levels, num_pts, num_groups
+    fd.pts_per_anchor = num_pts
+    return bool(_lib.lib().gf_daf_fused_supported(ctypes.byref(fd)))
+
+
+def deformable_aggregation_fused(mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weight_logits,
+                                 point_mask=None, weight_mask=None):
+    """Replacement for ``deformable_module.py:213-228`` + ``:242`` around the op call:
+
+    * ``weight_logits`` ``[B, A, K, M, L, Gr]`` — the raw weights after the permute at ``:177-189``
+    * ``point_mask`` ``[B, A, K, M]`` bool — ``mask.permute(0, 2, 3, 1)`` of ``project_points`` (``:211``)
+    * ``weight_mask`` ``[B, A, K, M, L, Gr]`` bool — the attn-drop mask (``:190-202``), or None in eval
+    * ``sampling_location`` ``[B, A*K, M, 2]`` — ``points_2d`` as passed to the op
+
+    Returns ``features.sum(dim=2)``: ``[B, A, C]``."""
+    return DeformableAggregationFusedFunction.apply(mc_ms_feat, spatial_shape, scale_start_index, sampling_location,
+                                                    weight_logits, point_mask, weight_mask)

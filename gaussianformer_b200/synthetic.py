@@ -151,3 +151,41 @@ def make_daf_inputs(num_anchor=25600, num_pts=9, batch=1, num_cams=6, embed_dims
     w = raw.flatten(2, 4).softmax(dim=-2).reshape(batch, P, num_cams, L, num_groups)
     w = w * (1 - all_miss.expand(-1, -1, num_pts, -1, -1, -1).reshape(batch, P, 1, 1, num_groups).float())
     return feature_maps, loc, w.contiguous()
+
+
+def make_daf_fused_inputs(num_anchor=25600, num_pts=9, batch=1, num_cams=6, embed_dims=128, num_groups=4,
+                          levels=DAF_LEVELS_1600x864, visible_p=0.22, seed=0, attn_drop=0.0):
+    """Inputs of the fused caller path (``ops.deformable_aggregation_fused``): the same pyramid and sampling
+    locations as ``make_daf_inputs`` plus what ``DeformableFeatureAggregation.forward`` holds BEFORE its softmax
+    (``deformable_module.py:177-212``): raw weights ``[B, A, K, M, L, Gr]``, the projection mask
+    ``[B, A, K, M]`` (a camera sees the key point) and, for ``attn_drop > 0``, the training-time weight mask."""
+    feature_maps, loc, _ = make_daf_inputs(num_anchor, num_pts, batch, num_cams, embed_dims, num_groups, levels,
+                                           visible_p, seed)
+    gen = torch.Generator().manual_seed(seed + 1000)
+    L = len(levels)
+    logits = torch.randn(batch, num_anchor, num_pts, num_cams, L, num_groups, generator=gen)
+    point_mask = ((loc > 0) & (loc < 1)).all(-1).reshape(batch, num_anchor, num_pts, num_cams).contiguous()
+    weight_mask = None
+    if attn_drop > 0:
+        weight_mask = torch.rand(logits.shape, generator=gen) > attn_drop
+    return feature_maps, loc, logits, point_mask, weight_mask
+
+
+def reference_fused_composition(daf_apply, feat, shape, start, loc, logits, point_mask=None, weight_mask=None):
+    """``deformable_module.py:213-228`` + ``:242`` in PyTorch around an op call ``daf_apply`` — what the fused entry
+    point replaces (used by the tests and by bench.py to time the unfused route on the same GPU)."""
+    B, A, K, M, L, Gr = logits.shape
+    mask = torch.ones_like(logits, dtype=torch.bool)
+    if point_mask is not None:
+        mask = point_mask[..., None, None] & mask
+    if weight_mask is not None:
+        mask = mask & weight_mask
+    all_miss = mask.sum(dim=[2, 3, 4], keepdim=True) == 0
+    all_miss = all_miss.expand(-1, -1, K, M, L, -1)
+    weights = logits.clone()
+    weights[~mask] = -torch.inf
+    weights[all_miss] = 0.
+    weights = weights.flatten(2, 4).softmax(dim=-2).reshape(B, A * K, M, L, Gr)
+    weights = weights * (1 - all_miss.flatten(1, 2).float())
+    features = daf_apply(feat, shape, start, loc, weights).reshape(B, A, K, -1)
+    return features.sum(dim=2)

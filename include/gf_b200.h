@@ -25,6 +25,11 @@
  *   gf_daf_backward    deformable_aggregation_grad()
  *                        .../ops/src/deformable_aggregation.cpp:20-38, ..._cuda.cu:287-313
  *
+ *   gf_daf_fused_*     no native counterpart in the reference: the op call above together with the PyTorch code
+ *                      around it in DeformableFeatureAggregation.forward
+ *                        model/encoder/gaussian_encoder/deformable_module.py:213-228 (masked joint softmax of
+ *                        the weights) and :242 (sum over the key points) -- an opt-in entry point
+ *
  * The ABI is a superset of those boundaries: explicit stream, explicit class count C (the
  * reference hard-codes NUM_CHANNELS 18, model/head/localagg/src/config.h:15), 64-bit safe sizes,
  * caller-owned workspace and an int status.
@@ -188,6 +193,43 @@ int gf_daf_backward(const gf_daf_desc *desc, const float *mc_ms_feat, const int3
  * gradient of the forward direction).  maps[l] are device pointers, the array itself lives on the host. */
 int gf_daf_format(const gf_daf_format_desc *desc, float *const *maps, float *table, int inverse,
                   gf_stream_t stream);
+
+/* ---- fused caller path of the deformable aggregation (opt-in; the entry points above stay the drop-in) ----
+ *
+ * For every anchor a (num_pts = A * pts_per_anchor sampling points per batch element, anchor-major) and
+ * group g, with e running over the anchor's (key point k, camera m, level l) entries:
+ *
+ *   on_e   = point_mask[b,a,k,m] (or 1 if NULL)  &  weight_mask[b,a,k,m,l,g] (or 1 if NULL)
+ *   w_e    = on_e ? exp(logit_e) / sum_{e' on} exp(logit_e') : 0        (all weights 0 when no entry is on)
+ *   out[b,a,c] = sum_k gf_daf_forward(...)[b, a*K + k, c]  evaluated with the weights w
+ *
+ * which is deformable_module.py:213-228 + :242 (weights[~mask] = -inf; weights[all_miss] = 0; softmax over the
+ * flattened (k, m, l) axis; * (1 - all_miss); DAF.apply; .sum(dim=2)).  Masks are bytes (0 / non-zero; a
+ * torch.bool tensor).  `stats` [B, A, Gr, 2] receives (max * log2(e), 1 / sum) per anchor and group and is what
+ * the backward needs besides the forward output.  Supported when gf_daf_fused_supported() != 0:
+ * num_embeds % 128 == 0, groups a power of two that divides num_embeds / 4 into power-of-two runs,
+ * num_cams * num_scale <= 32; other shapes return GF_ERR_UNSUPPORTED (use the unfused entry points). */
+typedef struct gf_daf_fused_desc {
+    gf_daf_desc d;
+    int32_t pts_per_anchor; /* K; d.num_pts % K == 0 */
+} gf_daf_fused_desc;
+
+int gf_daf_fused_supported(const gf_daf_fused_desc *desc);
+
+/* output [B, A, C] and stats [B, A, Gr, 2] are fully overwritten. */
+int gf_daf_fused_forward(const gf_daf_fused_desc *desc, const float *mc_ms_feat, const int32_t *spatial_shape,
+                         const int32_t *scale_start_index, const float *sample_location,
+                         const float *weight_logits, const uint8_t *point_mask, const uint8_t *weight_mask,
+                         float *output, float *stats, gf_stream_t stream);
+
+/* grad_weight_logits [B, A, K, M, L, Gr] is fully overwritten; grad_mc_ms_feat and grad_sampling_location are
+ * accumulated into (+=) like gf_daf_backward: the caller zero-fills them. */
+int gf_daf_fused_backward(const gf_daf_fused_desc *desc, const float *mc_ms_feat, const int32_t *spatial_shape,
+                          const int32_t *scale_start_index, const float *sample_location,
+                          const float *weight_logits, const uint8_t *point_mask, const uint8_t *weight_mask,
+                          const float *stats, const float *output, const float *grad_output,
+                          float *grad_mc_ms_feat, float *grad_sampling_location, float *grad_weight_logits,
+                          gf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -258,3 +258,47 @@ def daf_backward(feat, shape, start, loc, weights, g_out, precision="f32"):
                                              _p(loc), _p(weights), _p(g_out), _p(g_feat), _p(g_loc),
                                              _p(g_w))
     return g_feat, g_loc, g_w
+
+
+# --------------------------------------------------------------------------- fused caller path of the op
+def _fused_weights(logits, point_mask, weight_mask):
+    """The weight preparation of DeformableFeatureAggregation.forward
+    (model/encoder/gaussian_encoder/deformable_module.py:213-228), float64:
+    ``weights[~mask] = -inf; weights[all_miss] = 0; softmax over the flattened (K, M, L) axis;
+    weights * (1 - all_miss)``.  ``logits`` is [B, A, K, M, L, Gr]; returns (w [B, A, K, M, L, Gr], mask)."""
+    w = np.asarray(logits, np.float64)
+    B, A, K, M, L, Gr = w.shape
+    mask = np.ones(w.shape, bool)
+    if point_mask is not None:
+        mask &= np.asarray(point_mask, bool).reshape(B, A, K, M)[..., None, None]     # :213
+    if weight_mask is not None:
+        mask &= np.asarray(weight_mask, bool).reshape(w.shape)
+    all_miss = mask.sum(axis=(2, 3, 4), keepdims=True) == 0                            # :214
+    w = np.where(mask, w, -np.inf)                                                     # :216
+    w = np.where(all_miss, 0.0, w)                                                     # :217
+    flat = w.reshape(B, A, K * M * L, Gr)
+    flat = flat - flat.max(axis=2, keepdims=True)
+    e = np.exp(flat)
+    soft = (e / e.sum(axis=2, keepdims=True)).reshape(B, A, K, M, L, Gr)               # :218
+    return soft * (1.0 - all_miss), mask                                               # :228
+
+
+def daf_fused_forward(feat, shape, start, loc, logits, point_mask=None, weight_mask=None, precision="f64"):
+    """deformable_module.py:213-228 + the op (:226) + ``features.sum(dim=2)`` (:242) -> [B, A, C]."""
+    B, A, K, M, L, Gr = np.asarray(logits).shape
+    w, _ = _fused_weights(logits, point_mask, weight_mask)
+    out = daf_forward(feat, shape, start, loc, w.reshape(B, A * K, M, L, Gr), precision)
+    return out.reshape(B, A, K, -1).sum(axis=2)
+
+
+def daf_fused_backward(feat, shape, start, loc, logits, g_out, point_mask=None, weight_mask=None, precision="f64"):
+    """Chain rule through :242 (broadcast over key points), the op's own backward and the masked softmax.
+    Returns (g_feat, g_loc, g_logits)."""
+    B, A, K, M, L, Gr = np.asarray(logits).shape
+    w, _ = _fused_weights(logits, point_mask, weight_mask)
+    g_pts = np.repeat(np.asarray(g_out, np.float32)[:, :, None, :], K, axis=2).reshape(B, A * K, -1)
+    g_feat, g_loc, g_w = daf_backward(feat, shape, start, loc, w.reshape(B, A * K, M, L, Gr), g_pts, precision)
+    g_w = np.asarray(g_w, np.float64).reshape(B, A, K, M, L, Gr)
+    inner = (w * g_w).sum(axis=(2, 3, 4), keepdims=True)
+    # masked entries carry w = 0 (their logit was overwritten, :216-217) and all_miss groups have w = 0 throughout
+    return g_feat, g_loc, w * (g_w - inner)

@@ -101,3 +101,88 @@ def test_feature_maps_format_is_the_reference_layout(channels, levels):
     back = DAF.feature_maps_format([g, shape, start], inverse=True)      # the reference's inverse: views of g
     for m, b in zip(maps, back):
         assert torch.equal(m.grad, b.contiguous())
+
+
+# ------------------------------------------------------------------------------ fused caller path
+from gaussianformer_b200.ops import deformable_aggregation_fused, fused_supported  # noqa: E402
+from gaussianformer_b200.synthetic import make_daf_fused_inputs, reference_fused_composition  # noqa: E402
+
+
+@pytest.mark.parametrize("embed,groups,levels,masks", [
+    (128, 4, ((12, 20), (6, 10), (3, 5)), "both"),
+    (128, 4, ((12, 20), (6, 10), (3, 5)), "point"),
+    (128, 4, ((12, 20), (6, 10), (3, 5)), "none"),
+    (256, 8, ((9, 7), (5, 4)), "both"),                 # two channel slices per warp, 8 groups
+    (128, 1, ((5, 5),), "point"),                       # one group = the whole warp
+])
+def test_daf_fused_forward_backward_vs_oracle(embed, groups, levels, masks):
+    B, A, K, M = 2, 40, 5, 3
+    fms, loc, logits, pm, wm = make_daf_fused_inputs(num_anchor=A, num_pts=K, batch=B, num_cams=M, embed_dims=embed,
+                                                     num_groups=groups, levels=levels, visible_p=0.5, seed=21,
+                                                     attn_drop=0.15)
+    loc[0, 2, 0] = torch.tensor([0.004, 0.996]); loc[0, 3, 1] = torch.tensor([0.999, 0.001])
+    loc[1, 4, 2] = torch.tensor([float("nan"), 0.5])
+    pm = ((loc > 0) & (loc < 1)).all(-1).reshape(B, A, K, M).contiguous()
+    pm[0, 0] = False                                     # an anchor no camera sees
+    wm[0, 1, :, :, :, 0] = False                         # a group with every entry dropped
+    logits[1, 2, 0, 0, 0, 0] = 30.0                      # a dominant entry (softmax range)
+    if masks == "point":
+        wm = None
+    elif masks == "none":
+        pm = wm = None
+    assert fused_supported(embed, groups, M, len(levels))
+    feat, shape, start = DAF.feature_maps_format([f.cuda() for f in fms])
+    feat = feat.contiguous().requires_grad_()
+    loc_d = loc.cuda().requires_grad_()
+    lg_d = logits.cuda().requires_grad_()
+    out = deformable_aggregation_fused(feat, shape, start, loc_d, lg_d, None if pm is None else pm.cuda(),
+                                       None if wm is None else wm.cuda())
+    assert out.shape == (B, A, embed)
+    f_np, s_np, st_np = feat.detach().cpu().numpy(), shape.cpu().numpy(), start.cpu().numpy()
+    pm_np = None if pm is None else pm.numpy()
+    wm_np = None if wm is None else wm.numpy()
+    ref = oracle.daf_fused_forward(f_np, s_np, st_np, loc.numpy(), logits.numpy(), pm_np, wm_np, "f64")
+    h.assert_close(out.detach().cpu().numpy(), ref, what="fused daf out")
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    out.backward(g.cuda())
+    rf, rl, rw = oracle.daf_fused_backward(f_np, s_np, st_np, loc.numpy(), logits.numpy(), g.numpy(), pm_np, wm_np, "f64")
+    h.assert_close(feat.grad.cpu().numpy(), rf, rtol=1e-3, atol=h.grad_tolerance(rf), what="fused grad feat")
+    h.assert_close(lg_d.grad.cpu().numpy(), rw, rtol=1e-3, atol=h.grad_tolerance(rw), what="fused grad logits")
+    h.assert_close(loc_d.grad.cpu().numpy(), rl, rtol=1e-3, atol=h.grad_tolerance(rl), what="fused grad loc")
+    if pm is not None:
+        assert torch.all(out[0, 0] == 0) and torch.all(lg_d.grad[0, 0] == 0)
+
+
+def test_daf_fused_rejects_unsupported_shapes():
+    assert not fused_supported(16, 4, 3, 3)              # C % 128 != 0
+    assert not fused_supported(128, 4, 6, 8)             # more than 32 (camera, level) pairs
+    fms, loc, logits, pm, _ = make_daf_fused_inputs(num_anchor=8, num_pts=2, batch=1, num_cams=2, embed_dims=16,
+                                                    num_groups=4, levels=((4, 4),), seed=1)
+    feat, shape, start = DAF.feature_maps_format([f.cuda() for f in fms])
+    with pytest.raises(Exception, match="not supported"):
+        deformable_aggregation_fused(feat.contiguous(), shape, start, loc.cuda(), logits.cuda(), pm.cuda())
+
+
+def test_daf_fused_full_size_equals_the_unfused_route():
+    """BASELINE config-2 shape (25 600 anchors x 9 key points, 6 cameras, 4 levels, C = 128): the fused entry
+    point against the reference's composition (PyTorch masked softmax -> our drop-in op -> sum over key points)
+    on the same GPU, forward and backward."""
+    fms, loc, logits, pm, _ = make_daf_fused_inputs(seed=0)
+    feat, shape, start = DAF.feature_maps_format([f.cuda() for f in fms])
+    feat = feat.contiguous()
+    outs, grads = [], []
+    g = torch.randn(1, 25600, 128, generator=torch.Generator().manual_seed(2)).cuda()
+    for fused in (True, False):
+        f = feat.detach().clone().requires_grad_()
+        l = loc.cuda().requires_grad_()
+        w = logits.cuda().requires_grad_()
+        if fused:
+            out = deformable_aggregation_fused(f, shape, start, l, w, pm.cuda())
+        else:
+            out = reference_fused_composition(DAF.apply, f, shape, start, l, w, pm.cuda())
+        out.backward(g)
+        outs.append(out.detach().cpu().numpy())
+        grads.append([t.grad.cpu().numpy() for t in (f, l, w)])
+    h.assert_close(outs[0], outs[1], what="fused vs unfused out")
+    for name, a, b in zip(("feat", "loc", "logits"), grads[0], grads[1]):
+        h.assert_close(a, b, rtol=1e-3, atol=h.grad_tolerance(b), what="fused vs unfused grad " + name)

@@ -120,8 +120,10 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
     // come from the two preparation kernels, which this grid may have been launched ahead of.
     pdl_wait();
     if (stray) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
-    walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, [&](const float4 *r4, const float4 g0, const float4 g1, const float2 g2, uint32_t zb, bool active) {
+    walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, [&](const RecView rec, uint32_t zb, bool active) {
         if (active) {
+                    const float4 g0 = rec.chunk(0), g1 = rec.chunk(1), g2c = rec.chunk(2);
+                    const float2 g2 = make_float2(g2c.x, g2c.y);
                     float wv[VOX];
                     if (column) {
                         // My VOX points share x and y (voxel centres of one z column — every shipped config,
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
                     }
 #pragma unroll
                     for (int c4 = 0; c4 < (C + 3) / 4; ++c4) {
-                        const float4 s4 = r4[3 + c4];
+                        const float4 s4 = rec.chunk(3 + c4);
 #pragma unroll
                         for (int v = 0; v < VOX; ++v) {
                             const float2 ww = make_float2(wv[v], wv[v]);

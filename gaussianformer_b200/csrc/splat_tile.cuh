@@ -3,6 +3,8 @@
 // records through a shared-memory ring (Phase B) and calls `visit` for every record that touches the
 // calling warp's footprint, in ascending Gaussian order, with all 32 lanes converged.
 #pragma once
+#include <type_traits>
+
 #include "splat_render.cuh"
 
 namespace gf {
@@ -14,11 +16,20 @@ namespace gf {
 #define GF_RENDER_VOX 4   // voxels per thread of the tile kernel (2 or 4)
 #endif
 constexpr int kQuadSeg = 512;   // list entries resolved per segment
-constexpr int kBatch = 32;      // records staged per ring slot
+#ifndef GF_TILE_BATCH
+#define GF_TILE_BATCH 32
+#endif
+constexpr int kBatch = GF_TILE_BATCH;   // records staged per ring slot (32 or 64; 64 needs GF_TILE_LANEWALK)
+static_assert(kBatch == 32 || kBatch == 64, "a lane keeps its hit mask of a batch in one 32- or 64-bit word");
 #ifndef GF_TILE_RING
 #define GF_TILE_RING 5   // measured: 5, 6, 7 slots 72.0 us per step, 4 and 8 slots 73.4 us
 #endif
 constexpr int kRing = GF_TILE_RING;   // ring slots: a warp may run up to kRing-2 batches ahead of the slowest one
+// 1: every lane walks its OWN hits of a batch (lane-private traversal, see walk_tile); 0: the warp visits every
+// record that touches its footprint with all lanes on the same record (first generation)
+#ifndef GF_TILE_LANEWALK
+#define GF_TILE_LANEWALK 1
+#endif
 
 template <int C, int VOX>
 struct RenderSmem {
@@ -43,9 +54,30 @@ __device__ __forceinline__ void mbar_arrive_one(uint64_t *bar) {
 }
 
 
-// visit(const float4 *record, float4 g0, float4 g1, float2 g2, uint32_t zbits, bool active): g0..g2 are the
-// record's geometry words (already loaded), `active` says whether this lane's column lies inside the
-// Gaussian's box; bit v of zbits whether its voxel v does.
+// One staged record as a lane sees it: a 128-byte slot whose eight 16-byte chunks are stored XOR-swizzled by the
+// slot's row (chunk c of row j sits at position c ^ (j & 7)), so that lanes of one warp reading the same chunk of
+// DIFFERENT records fall into different bank groups.  `addr` is the shared-space address of the row with the
+// swizzle already folded in (the row is 128-byte aligned, so the fold is an OR), chunk i is one XOR away.
+struct RecView {
+    uint32_t addr;
+    __device__ __forceinline__ float4 chunk(int i) const {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr ^ (static_cast<uint32_t>(i) << 4)));
+        return v;
+    }
+};
+
+// visit(RecView record, uint32_t zbits, bool active): `active` says whether this lane has a record to evaluate in
+// this step (its column lies inside the Gaussian's box and at least one of its voxels does); bit v of zbits
+// whether its voxel v does.  Inactive lanes must not touch `record`.
+//
+// Lane-private traversal (GF_TILE_LANEWALK): a Gaussian's box covers only part of a warp's 4 x 4 x 2*VOX
+// footprint (17.7 of 32 lanes on the nuScenes workload), so marching all lanes through every record that touches
+// the footprint leaves almost half of them idle in every step.  Instead each lane gets the bit mask of the
+// records of the batch that cover ITS column and z group -- the box masks are separable, so ten ballots
+// (4 x bits, 4 y bits, 2 z groups) and three selects produce all 32 masks -- and walks its own bits in ascending
+// order (the reference's summation order per voxel); the warp iterates max-over-lanes popcount times instead of
+// once per touching record, and every step does useful work in every lane that still has hits.
 template <int C, int VOX, class Visit>
 __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, VOX> &sm, int binX0, int binY0, int binZ0,
                                           uint32_t my_xy, int my_zshift, Visit &&visit) {
@@ -55,6 +87,7 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.d.H, W = p.d.W, D = p.d.D;
     if (tid == 0) {
+        if (smem_u32(&sm.stage[0][0]) & 127u) __trap();   // RecView folds the swizzle into the address with an OR
 #pragma unroll
         for (int r = 0; r < kRing; ++r) {
             mbar_init(&sm.bar_full[r], NT);
@@ -143,7 +176,8 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
                 const int piece = tid + NT * q, row = piece >> 3, col = (piece & 7) * 4;
                 if (piece < kBatch * 8 && k * kBatch + row < nlist) {
                     const uint32_t g = sm.list[k * kBatch + row].y & 0x00FFFFFFu;
-                    cp_async16(&sm.stage[slot][row * REC + col], p.records + static_cast<size_t>(g) * REC + col);
+                    const int dcol = (((piece & 7) ^ (row & 7)) * 4);      // swizzled chunk position (see RecView)
+                    cp_async16(&sm.stage[slot][row * REC + dcol], p.records + static_cast<size_t>(g) * REC + col);
                 }
             }
             cp_async_arrive_on(&sm.bar_full[slot]);
@@ -153,6 +187,42 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
 #pragma unroll 1
         for (int k = 0; k < nchunks; ++k, ++gb) {
             const int slot = gb % kRing;
+            const uint32_t stage_base = smem_u32(&sm.stage[slot][0]);
+#if GF_TILE_LANEWALK
+            // bit j of `hits`: record j of this batch covers my column and my z group (padded entries are all-zero)
+            using HitMask = typename std::conditional<kBatch == 64, unsigned long long, uint32_t>::type;
+            const int xh = 4 * (warp & 1), zg = 16 + 2 * VOX * (warp >> 1);
+            const int sx = lane >> 3, sy = (lane >> 1) & 3;
+            HitMask hits = 0;
+#pragma unroll
+            for (int h = 0; h < kBatch / 32; ++h) {
+                const uint32_t ex = sm.list[k * kBatch + 32 * h + lane].x;
+                uint32_t bx[4], by[4], bz[2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    bx[i] = __ballot_sync(0xffffffffu, (ex >> (xh + i)) & 1u);
+                    by[i] = __ballot_sync(0xffffffffu, (ex >> (8 + i)) & 1u);
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) bz[q] = __ballot_sync(0xffffffffu, ((ex >> (zg + VOX * q)) & VMASK) != 0u);
+                const uint32_t word = (sx == 0 ? bx[0] : sx == 1 ? bx[1] : sx == 2 ? bx[2] : bx[3]) &
+                                      (sy == 0 ? by[0] : sy == 1 ? by[1] : sy == 2 ? by[2] : by[3]) & ((lane & 1) ? bz[1] : bz[0]);
+                hits |= static_cast<HitMask>(word) << (32 * h);
+            }
+            mbar_wait(&sm.bar_full[slot], (gb / kRing) & 1);
+            while (__any_sync(0xffffffffu, hits != 0)) {
+                const bool act = hits != 0;
+                int j = 0;
+                if (kBatch == 64) j = act ? __ffsll(static_cast<long long>(hits)) - 1 : 0;
+                else j = act ? __ffs(static_cast<int>(hits)) - 1 : 0;
+                hits &= hits - 1;                                    // 0 stays 0
+                const uint32_t e = sm.list[k * kBatch + j].x;
+                RecView rv;
+                rv.addr = stage_base + static_cast<uint32_t>(j) * (REC * 4) + ((static_cast<uint32_t>(j) & 7u) << 4);
+                visit(rv, (e >> my_zshift) & VMASK, act);
+            }
+#else
+            static_assert(kBatch == 32, "the first-generation walk keeps one hit word per batch");
             // records that touch my warp's footprint, in ascending order (the hit bits are gathered before the
             // wait for the records).  Fetching the next hit's entry / geometry ahead of the current visit was
             // measured slower (75.3 / 81.4 vs 73.4 us per step): the registers it takes cost more than the
@@ -165,9 +235,11 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
                 todo &= todo - 1;
                 const uint32_t e = sm.list[k * kBatch + j].x;
                 const uint32_t zb = (e >> my_zshift) & VMASK;
-                const float4 *r4 = reinterpret_cast<const float4 *>(&sm.stage[slot][j * REC]);
-                visit(r4, r4[0], r4[1], *reinterpret_cast<const float2 *>(r4 + 2), zb, (e & my_xy) == my_xy && zb != 0u);
+                RecView rv;
+                rv.addr = stage_base + static_cast<uint32_t>(j) * (REC * 4) + ((static_cast<uint32_t>(j) & 7u) << 4);
+                visit(rv, zb, (e & my_xy) == my_xy && zb != 0u);
             }
+#endif
             __syncwarp();
             if (lane == 0) mbar_arrive_one(&sm.bar_empty[slot]);       // my warp is done with this slot
             if (k + kRing - 1 < nchunks) issue(k + kRing - 1, gb + kRing - 1);

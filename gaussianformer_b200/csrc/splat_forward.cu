@@ -37,7 +37,11 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
 
     // ---- which voxels are mine -------------------------------------------------------------------
     const int binX0 = blockIdx.z * kBinX, binY0 = blockIdx.y * kBinY, binZ0 = blockIdx.x * kBinZ;
+#if GF_TILE_MAP == 1
+    const int lx = lane & 7, ly = lane >> 3, lq = warp;                                                    // z group
+#else
     const int lx = (warp & 1) * 4 + (lane >> 3), ly = (lane >> 1) & 3, lq = (warp >> 1) * 2 + (lane & 1);  // z group
+#endif
     const int X = binX0 + lx, Y = binY0 + ly, Z0 = binZ0 + VOX * lq;
     const bool col_ok = X < H && Y < W;
     const long long n0 = (static_cast<long long>(X) * W + Y) * D + Z0;
@@ -120,67 +124,89 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
     // come from the two preparation kernels, which this grid may have been launched ahead of.
     pdl_wait();
     if (stray) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
-    walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, [&](const RecView rec, uint32_t zb, bool active) {
-        if (active) {
-                    const float4 g0 = rec.chunk(0), g1 = rec.chunk(1), g2c = rec.chunk(2);
-                    const float2 g2 = make_float2(g2c.x, g2c.y);
-                    float wv[VOX];
-                    if (column) {
-                        // My VOX points share x and y (voxel centres of one z column — every shipped config,
-                        // dataset/transform_3d.py:484-499 without perturbation): the exponent is a quadratic
-                        // in dz alone, q = (cc*dz + B)*dz + A, with A and B evaluated once per record.
-                        const float dx = g0.x - px[0], dy = g0.y - py[0];
-                        float t1 = g1.x * dx;
-                        t1 = fmaf(g1.w, dy, t1);
-                        float A = t1 * dx;
-                        A = fmaf(g1.y * dy, dy, A);
-                        const float B = fmaf(g2.x, dy, g2.y * dx);
+    // One step of a lane = one (record, my VOX voxels) evaluation, in two stages so that the walker can overlap the
+    // loads of the next step with the arithmetic of the current one:
+    //   stage_e    exponent and weight of my voxels from the record's geometry chunks; starts the loads of its class chunks
+    //   stage_acc  the class accumulation (VOX x C/2 packed FMAs) with the weights / class chunks of the last stage_e
+    float wv[VOX];
+#if GF_TILE_PIPE
+    float4 cls[(C + 3) / 4];
+#else
+    RecView cur_rec;   // without the pipeline the class chunks are read where they are used (fewer live registers)
+    cur_rec.addr = 0;
+#endif
+    auto stage_e = [&](const float4 g0, const float4 g1, const float4 g2c, const RecView rec, uint32_t zb, bool active) {
+        if (!active) return;
+#if GF_TILE_PIPE
 #pragma unroll
-                        for (int v = 0; v < VOX; ++v) {
-                            const float dz = g0.z - pz[v];
-                            const float q = fmaf(fmaf(g1.z, dz, B), dz, A);
-                            const float E = ((zb >> v) & 1u) ? ex2_approx(q) : 0.f;
-                            wv[v] = g0.w * E;
-                            if (PROB) { zsum[v] += wv[v]; dens[v] += E; keep[v] *= (1.f - E); }
-                        }
-                    } else {
-                    // general points: quadratic form on packed fp32 pairs, voxels (0,1) and (2,3) share each instruction
+        for (int c4 = 0; c4 < (C + 3) / 4; ++c4) cls[c4] = rec.chunk(3 + c4);
+#else
+        cur_rec = rec;
+#endif
+        const float2 g2 = make_float2(g2c.x, g2c.y);
+        if (column) {
+            // My VOX points share x and y (voxel centres of one z column — every shipped config,
+            // dataset/transform_3d.py:484-499 without perturbation): the exponent is a quadratic
+            // in dz alone, q = (cc*dz + B)*dz + A, with A and B evaluated once per record.
+            const float dx = g0.x - px[0], dy = g0.y - py[0];
+            float t1 = g1.x * dx;
+            t1 = fmaf(g1.w, dy, t1);
+            float A = t1 * dx;
+            A = fmaf(g1.y * dy, dy, A);
+            const float B = fmaf(g2.x, dy, g2.y * dx);
 #pragma unroll
-                    for (int h2 = 0; h2 < VOX / 2; ++h2) {
-                        const int v0 = 2 * h2, v1 = v0 + 1;
-                        const float2 dx = __fadd2_rn(make_float2(g0.x, g0.x), make_float2(-px[v0], -px[v1]));
-                        const float2 dy = __fadd2_rn(make_float2(g0.y, g0.y), make_float2(-py[v0], -py[v1]));
-                        const float2 dz = __fadd2_rn(make_float2(g0.z, g0.z), make_float2(-pz[v0], -pz[v1]));
-                        float2 t1 = __fmul2_rn(make_float2(g1.x, g1.x), dx);
-                        t1 = __ffma2_rn(make_float2(g1.w, g1.w), dy, t1);
-                        t1 = __ffma2_rn(make_float2(g2.y, g2.y), dz, t1);
-                        float2 t2 = __fmul2_rn(make_float2(g1.y, g1.y), dy);
-                        t2 = __ffma2_rn(make_float2(g2.x, g2.x), dz, t2);
-                        float2 q = __fmul2_rn(t1, dx);
-                        q = __ffma2_rn(t2, dy, q);
-                        q = __ffma2_rn(__fmul2_rn(make_float2(g1.z, g1.z), dz), dz, q);
-                        const float E0 = ((zb >> v0) & 1u) ? ex2_approx(q.x) : 0.f;
-                        const float E1 = ((zb >> v1) & 1u) ? ex2_approx(q.y) : 0.f;
-                        wv[v0] = g0.w * E0;
-                        wv[v1] = g0.w * E1;
-                        if (PROB) {
-                            zsum[v0] += wv[v0]; dens[v0] += E0; keep[v0] *= (1.f - E0);
-                            zsum[v1] += wv[v1]; dens[v1] += E1; keep[v1] *= (1.f - E1);
-                        }
-                    }
-                    }
+            for (int v = 0; v < VOX; ++v) {
+                const float dz = g0.z - pz[v];
+                const float q = fmaf(fmaf(g1.z, dz, B), dz, A);
+                const float E = ((zb >> v) & 1u) ? ex2_approx(q) : 0.f;
+                wv[v] = PROB ? g0.w * E : E;      // base: the opacity is folded into the class vector (pack kernel)
+                if (PROB) { zsum[v] += wv[v]; dens[v] += E; keep[v] *= (1.f - E); }
+            }
+        } else {
+            // general points: quadratic form on packed fp32 pairs, voxels (0,1) and (2,3) share each instruction
 #pragma unroll
-                    for (int c4 = 0; c4 < (C + 3) / 4; ++c4) {
-                        const float4 s4 = rec.chunk(3 + c4);
+            for (int h2 = 0; h2 < VOX / 2; ++h2) {
+                const int v0 = 2 * h2, v1 = v0 + 1;
+                const float2 dx = __fadd2_rn(make_float2(g0.x, g0.x), make_float2(-px[v0], -px[v1]));
+                const float2 dy = __fadd2_rn(make_float2(g0.y, g0.y), make_float2(-py[v0], -py[v1]));
+                const float2 dz = __fadd2_rn(make_float2(g0.z, g0.z), make_float2(-pz[v0], -pz[v1]));
+                float2 t1 = __fmul2_rn(make_float2(g1.x, g1.x), dx);
+                t1 = __ffma2_rn(make_float2(g1.w, g1.w), dy, t1);
+                t1 = __ffma2_rn(make_float2(g2.y, g2.y), dz, t1);
+                float2 t2 = __fmul2_rn(make_float2(g1.y, g1.y), dy);
+                t2 = __ffma2_rn(make_float2(g2.x, g2.x), dz, t2);
+                float2 q = __fmul2_rn(t1, dx);
+                q = __ffma2_rn(t2, dy, q);
+                q = __ffma2_rn(__fmul2_rn(make_float2(g1.z, g1.z), dz), dz, q);
+                const float E0 = ((zb >> v0) & 1u) ? ex2_approx(q.x) : 0.f;
+                const float E1 = ((zb >> v1) & 1u) ? ex2_approx(q.y) : 0.f;
+                wv[v0] = PROB ? g0.w * E0 : E0;
+                wv[v1] = PROB ? g0.w * E1 : E1;
+                if (PROB) {
+                    zsum[v0] += wv[v0]; dens[v0] += E0; keep[v0] *= (1.f - E0);
+                    zsum[v1] += wv[v1]; dens[v1] += E1; keep[v1] *= (1.f - E1);
+                }
+            }
+        }
+    };
+    auto stage_acc = [&](bool active) {
+        if (!active) return;
 #pragma unroll
-                        for (int v = 0; v < VOX; ++v) {
-                            const float2 ww = make_float2(wv[v], wv[v]);
-                            acc[v][2 * c4] = __ffma2_rn(make_float2(s4.x, s4.y), ww, acc[v][2 * c4]);
-                            if (2 * c4 + 1 < CP2) acc[v][2 * c4 + 1] = __ffma2_rn(make_float2(s4.z, s4.w), ww, acc[v][2 * c4 + 1]);
-                        }
-                    }
-                        }
-    });
+        for (int c4 = 0; c4 < (C + 3) / 4; ++c4) {
+#if GF_TILE_PIPE
+            const float4 s4 = cls[c4];
+#else
+            const float4 s4 = cur_rec.chunk(3 + c4);
+#endif
+#pragma unroll
+            for (int v = 0; v < VOX; ++v) {
+                const float2 ww = make_float2(wv[v], wv[v]);
+                acc[v][2 * c4] = __ffma2_rn(make_float2(s4.x, s4.y), ww, acc[v][2 * c4]);
+                if (2 * c4 + 1 < CP2) acc[v][2 * c4 + 1] = __ffma2_rn(make_float2(s4.z, s4.w), ww, acc[v][2 * c4 + 1]);
+            }
+        }
+    };
+    walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, stage_e, stage_acc);
 
     // ---- epilogue ----------------------------------------------------------------------------------
     if (!(col_ok && Z0 < D)) return;

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
                     const bool in = (e & my_bits) == my_bits;
                     const float Eraw = ex2_approx(q);
                     const float E = in ? Eraw : 0.f;          // select AFTER the arithmetic: padded slots hold
-                    w[j] = in ? g0.w * Eraw : 0.f;            // stale bytes and must never leak a NaN into W
+                    w[j] = in ? (PROB ? g0.w * Eraw : Eraw) : 0.f;   // stale bytes and must never leak a NaN into W (base: opacity is in S)
                     if (PROB) {
                         dens += E;
                         keep *= (1.f - E);

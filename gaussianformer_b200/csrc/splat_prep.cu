@@ -80,6 +80,11 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
             // (2*pi)^-1.5 * sqrt(det) * opacity   (localagg_prob/src/forward.cu:77-78)
             const float det = a_ * b_ * c_ + 2.f * d_ * e_ * f_ - a_ * e_ * e_ - b_ * f_ * f_ - c_ * d_ * d_;
             amp = kKappa * sqrtf(det) * amp;
+        } else {
+            // base variant: out = sum_g (o_g s_g) E_g -- the opacity rides in the class vector, the render kernels
+            // multiply by E alone (one multiply per Gaussian here instead of one per (voxel, Gaussian) pair there)
+#pragma unroll
+            for (int i = 0; i < 20; ++i) semv[i] *= amp;
         }
         float4 *rec = reinterpret_cast<float4 *>(p.records + static_cast<size_t>(g) * p.rec);
         rec[0] = make_float4(mu[0], mu[1], mu[2], amp);

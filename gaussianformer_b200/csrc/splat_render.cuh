@@ -78,7 +78,7 @@ __device__ __forceinline__ void render_one_point(const RenderParams &p, long lon
             q = fmaf(t2, dy, q);
             q = fmaf(g1.z * dz, dz, q);
             const float E = ex2_approx(q);
-            const float w = g0.w * E;
+            const float w = PROB ? g0.w * E : E;   // base: the class vector of the record already carries the opacity
             if (PROB) {
                 zsum += w;
                 dens += E;

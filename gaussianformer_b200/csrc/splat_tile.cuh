@@ -16,6 +16,14 @@ namespace gf {
 #define GF_RENDER_VOX 4   // voxels per thread of the tile kernel (2 or 4)
 #endif
 constexpr int kQuadSeg = 512;   // list entries resolved per segment
+// lane -> voxel mapping of a warp: 0 = 4 x 4 columns x two z groups (first generation), 1 = the bin's 8 x 4 columns
+// at ONE z group per warp (lanes of a warp then see the same z statistics: ~6 % fewer walk steps)
+#ifndef GF_TILE_MAP
+#define GF_TILE_MAP 0
+#endif
+#ifndef GF_TILE_PIPE
+#define GF_TILE_PIPE 0
+#endif
 #ifndef GF_TILE_BATCH
 #define GF_TILE_BATCH 32
 #endif
@@ -67,9 +75,14 @@ struct RecView {
     }
 };
 
-// visit(RecView record, uint32_t zbits, bool active): `active` says whether this lane has a record to evaluate in
-// this step (its column lies inside the Gaussian's box and at least one of its voxels does); bit v of zbits
-// whether its voxel v does.  Inactive lanes must not touch `record`.
+// The caller supplies the two stages of a lane's step:
+//   stage_e(float4 g0, float4 g1, float4 g2, RecView record, uint32_t zbits, bool active)   geometry chunks 0..2 (already
+//       loaded) -> weights; `active` says whether this lane has a record to evaluate in this step (its column lies
+//       inside the Gaussian's box and at least one of its voxels does); bit v of zbits whether its voxel v does.
+//       Inactive lanes must not touch `record`.
+//   stage_acc(bool active)   accumulate with what the last stage_e left behind.
+// GF_TILE_PIPE = 1 software-pipelines the two: the geometry of a lane's NEXT hit is requested before stage_acc of the
+// current one, so its shared-memory latency hides behind the accumulation instead of stalling the next exponent.
 //
 // Lane-private traversal (GF_TILE_LANEWALK): a Gaussian's box covers only part of a warp's 4 x 4 x 2*VOX
 // footprint (17.7 of 32 lanes on the nuScenes workload), so marching all lanes through every record that touches
@@ -78,9 +91,9 @@ struct RecView {
 // (4 x bits, 4 y bits, 2 z groups) and three selects produce all 32 masks -- and walks its own bits in ascending
 // order (the reference's summation order per voxel); the warp iterates max-over-lanes popcount times instead of
 // once per touching record, and every step does useful work in every lane that still has hits.
-template <int C, int VOX, class Visit>
+template <int C, int VOX, class StageE, class StageAcc>
 __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, VOX> &sm, int binX0, int binY0, int binZ0,
-                                          uint32_t my_xy, int my_zshift, Visit &&visit) {
+                                          uint32_t my_xy, int my_zshift, StageE &&stage_e, StageAcc &&stage_acc) {
     constexpr int REC = rec_floats(C);
     constexpr int NT = 512 / VOX, NWARP = NT / 32;
     constexpr uint32_t VMASK = (1u << VOX) - 1u;
@@ -191,12 +204,25 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
 #if GF_TILE_LANEWALK
             // bit j of `hits`: record j of this batch covers my column and my z group (padded entries are all-zero)
             using HitMask = typename std::conditional<kBatch == 64, unsigned long long, uint32_t>::type;
-            const int xh = 4 * (warp & 1), zg = 16 + 2 * VOX * (warp >> 1);
-            const int sx = lane >> 3, sy = (lane >> 1) & 3;
             HitMask hits = 0;
 #pragma unroll
             for (int h = 0; h < kBatch / 32; ++h) {
                 const uint32_t ex = sm.list[k * kBatch + 32 * h + lane].x;
+#if GF_TILE_MAP == 1
+                uint32_t bx[8], by[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bx[i] = __ballot_sync(0xffffffffu, (ex >> i) & 1u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) by[i] = __ballot_sync(0xffffffffu, (ex >> (8 + i)) & 1u);
+                const uint32_t bzq = __ballot_sync(0xffffffffu, ((ex >> (16 + VOX * warp)) & VMASK) != 0u);
+                const int sx = lane & 7, sy = lane >> 3;
+                const uint32_t x03 = (sx & 2) ? ((sx & 1) ? bx[3] : bx[2]) : ((sx & 1) ? bx[1] : bx[0]);
+                const uint32_t x47 = (sx & 2) ? ((sx & 1) ? bx[7] : bx[6]) : ((sx & 1) ? bx[5] : bx[4]);
+                const uint32_t word = ((sx & 4) ? x47 : x03) &
+                                      (sy == 0 ? by[0] : sy == 1 ? by[1] : sy == 2 ? by[2] : by[3]) & bzq;
+#else
+                const int xh = 4 * (warp & 1), zg = 16 + 2 * VOX * (warp >> 1);
+                const int sx = lane >> 3, sy = (lane >> 1) & 3;
                 uint32_t bx[4], by[4], bz[2];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -207,22 +233,50 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
                 for (int q = 0; q < 2; ++q) bz[q] = __ballot_sync(0xffffffffu, ((ex >> (zg + VOX * q)) & VMASK) != 0u);
                 const uint32_t word = (sx == 0 ? bx[0] : sx == 1 ? bx[1] : sx == 2 ? bx[2] : bx[3]) &
                                       (sy == 0 ? by[0] : sy == 1 ? by[1] : sy == 2 ? by[2] : by[3]) & ((lane & 1) ? bz[1] : bz[0]);
+#endif
                 hits |= static_cast<HitMask>(word) << (32 * h);
             }
             mbar_wait(&sm.bar_full[slot], (gb / kRing) & 1);
-            while (__any_sync(0xffffffffu, hits != 0)) {
-                const bool act = hits != 0;
+            auto next_hit = [&](bool &act, RecView &rv, uint32_t &zb) {   // pops my lowest remaining hit
+                act = hits != 0;
                 int j = 0;
                 if (kBatch == 64) j = act ? __ffsll(static_cast<long long>(hits)) - 1 : 0;
                 else j = act ? __ffs(static_cast<int>(hits)) - 1 : 0;
                 hits &= hits - 1;                                    // 0 stays 0
                 const uint32_t e = sm.list[k * kBatch + j].x;
-                RecView rv;
                 rv.addr = stage_base + static_cast<uint32_t>(j) * (REC * 4) + ((static_cast<uint32_t>(j) & 7u) << 4);
-                visit(rv, (e >> my_zshift) & VMASK, act);
+                zb = (e >> my_zshift) & VMASK;
+            };
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#if GF_TILE_PIPE
+            bool act_c, act_n;
+            RecView rv;
+            uint32_t zb;
+            float4 g0 = zero4, g1 = zero4, g2 = zero4;
+            next_hit(act_c, rv, zb);
+            if (act_c) { g0 = rv.chunk(0); g1 = rv.chunk(1); g2 = rv.chunk(2); }
+            stage_e(g0, g1, g2, rv, zb, act_c);
+            while (__any_sync(0xffffffffu, act_c)) {
+                next_hit(act_n, rv, zb);
+                if (act_n) { g0 = rv.chunk(0); g1 = rv.chunk(1); g2 = rv.chunk(2); }   // in flight during the accumulation
+                stage_acc(act_c);
+                stage_e(g0, g1, g2, rv, zb, act_n);
+                act_c = act_n;
             }
 #else
-            static_assert(kBatch == 32, "the first-generation walk keeps one hit word per batch");
+            while (__any_sync(0xffffffffu, hits != 0)) {
+                bool act;
+                RecView rv;
+                uint32_t zb;
+                next_hit(act, rv, zb);
+                float4 g0 = zero4, g1 = zero4, g2 = zero4;
+                if (act) { g0 = rv.chunk(0); g1 = rv.chunk(1); g2 = rv.chunk(2); }
+                stage_e(g0, g1, g2, rv, zb, act);
+                stage_acc(act);
+            }
+#endif
+#else
+            static_assert(kBatch == 32 && GF_TILE_MAP == 0, "the first-generation walk: one hit word per batch, warp-hit bits of mapping 0");
             // records that touch my warp's footprint, in ascending order (the hit bits are gathered before the
             // wait for the records).  Fetching the next hit's entry / geometry ahead of the current visit was
             // measured slower (75.3 / 81.4 vs 73.4 us per step): the registers it takes cost more than the
@@ -237,7 +291,12 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
                 const uint32_t zb = (e >> my_zshift) & VMASK;
                 RecView rv;
                 rv.addr = stage_base + static_cast<uint32_t>(j) * (REC * 4) + ((static_cast<uint32_t>(j) & 7u) << 4);
-                visit(rv, zb, (e & my_xy) == my_xy && zb != 0u);
+                const bool act = (e & my_xy) == my_xy && zb != 0u;
+                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 g0 = zero4, g1 = zero4, g2 = zero4;
+                if (act) { g0 = rv.chunk(0); g1 = rv.chunk(1); g2 = rv.chunk(2); }
+                stage_e(g0, g1, g2, rv, zb, act);
+                stage_acc(act);
             }
 #endif
             __syncwarp();

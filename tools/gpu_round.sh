@@ -1,16 +1,24 @@
 #!/bin/bash
-# One GPU visit: parity tests, then A/B bench lines of the render-kernel variants, then the side measurements.
-# Usage (through gpurun): bash tools/gpu_round.sh <tag>
+# One GPU visit: parity tests, then A/B bench lines of the render-kernel variants (libraries built by
+# tools/build_variant.py), optionally ncu captures.  Usage (through gpurun):
+#   bash tools/gpu_round.sh <tag> "<variants>" [tests] [ncu] [full]
 set +e
-tag=${1:-x}
+tag=${1:-x}; variants=${2:-default}; shift 2
 out=gpurun_out/$tag
 mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/smi.txt 2>&1
-timeout 1200 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1
-echo "pytest rc=$?" >> $out/pytest.log
-tail -5 $out/pytest.log
-for v in default walk0 b64; do
+for what in "$@"; do
+  if [ $what = tests ]; then
+    timeout 1200 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1
+    echo "pytest rc=$?" >> $out/pytest.log
+    tail -5 $out/pytest.log
+  fi
+done
+for v in $variants; do
   if [ $v = default ]; then unset GF_B200_LIB; else export GF_B200_LIB=$PWD/gaussianformer_b200/csrc/variants/libgf_b200_$v.so; fi
+  if [ $v != default ]; then
+    timeout 600 python -m pytest tests/test_splat_gpu.py tests/test_cabi_gpu.py -m gpu -x -q 2>&1 | tail -1 | sed "s/^/$v parity: /"
+  fi
   for rep in 1 2; do
     timeout 300 python bench.py --steps 200 --warmup 20 --no-extras > $out/bench_${v}_$rep.json 2> $out/bench_${v}_$rep.err
     python - <<PY
@@ -24,5 +32,16 @@ PY
   done
 done
 unset GF_B200_LIB
-timeout 600 python bench.py --steps 200 --warmup 20 > $out/bench_full.json 2> $out/bench_full.err
-tail -c 3000 $out/bench_full.json
+for what in "$@"; do
+  if [ $what = ncu ]; then
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
+        python bench.py --steps 6 --warmup 3 --no-extras > $out/ncu_launch.log 2>&1
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_tile -s 4 -c 2 -o $out/render_full -f \
+        python bench.py --steps 6 --warmup 3 --no-extras > $out/ncu_full.log 2>&1
+    ls -la $out | tail -5
+  fi
+  if [ $what = full ]; then
+    timeout 600 python bench.py --steps 200 --warmup 20 > $out/bench_full.json 2> $out/bench_full.err
+    tail -c 1500 $out/bench_full.json
+  fi
+done

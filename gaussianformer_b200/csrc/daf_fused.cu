@@ -63,6 +63,10 @@ __global__ void __launch_bounds__(kDafThreads, BACKWARD ? 3 : 4) daf_fused_kerne
     PairSetup *mine = s_pair[warp];
     const int my_cam = lane / L, my_lv = lane - my_cam * L;
     const int eg = lane & (Gr - 1);                      // group of the entries this lane sweeps (Gr | 32)
+    // point-mask index of entry e = lane + 32*it is e / (L*Gr); when L*Gr divides 32 that is it*pm_step + pm_sub
+    // without a division in the sweeps (L*Gr = 16 at the shipped shapes)
+    const bool pm_fast = LG <= 32 && (32 % LG) == 0;
+    const int pm_step = pm_fast ? 32 / LG : 0, pm_sub = pm_fast ? lane / LG : 0;
 
     for (long long ba = static_cast<long long>(blockIdx.x) * kWarps + warp; ba < nanchor; ba += warps) {
         const int b = static_cast<int>(ba / A);
@@ -73,15 +77,15 @@ __global__ void __launch_bounds__(kDafThreads, BACKWARD ? 3 : 4) daf_fused_kerne
         // ---- softmax statistics of the anchor: max and 1/sum per group over its K*M*L unmasked entries -----
         if (!BACKWARD) {
             float mx = -INFINITY;
-            for (int e = lane; e < nE; e += 32) {
-                const bool on = (!pm || pm[e / LG]) && (!wm || wm[e]);
+            for (int e = lane, it = 0; e < nE; e += 32, ++it) {
+                const bool on = (!pm || pm[pm_fast ? it * pm_step + pm_sub : e / LG]) && (!wm || wm[e]);
                 if (on) mx = fmaxf(mx, __ldg(wl + e));
             }
             for (int o = Gr; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             const float mlog = (mx == -INFINITY) ? 0.f : mx * kLog2e;
             float sum = 0.f;
-            for (int e = lane; e < nE; e += 32) {
-                const bool on = (!pm || pm[e / LG]) && (!wm || wm[e]);
+            for (int e = lane, it = 0; e < nE; e += 32, ++it) {
+                const bool on = (!pm || pm[pm_fast ? it * pm_step + pm_sub : e / LG]) && (!wm || wm[e]);
                 if (on) sum += ex2_approx(fmaf(__ldg(wl + e), kLog2e, -mlog));
             }
             for (int o = Gr; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -113,8 +117,8 @@ __global__ void __launch_bounds__(kDafThreads, BACKWARD ? 3 : 4) daf_fused_kerne
         if (BACKWARD) {
             // every entry as if its sample were zero: dL/dlogit_e = -w_e * S_g; visited pairs overwrite theirs below
             const float mlog = s_mlog[warp][eg], inv = s_inv[warp][eg], S = s_dot[warp][eg];
-            for (int e = lane; e < nE; e += 32) {
-                const bool on = (!pm || pm[e / LG]) && (!wm || wm[e]);
+            for (int e = lane, it = 0; e < nE; e += 32, ++it) {
+                const bool on = (!pm || pm[pm_fast ? it * pm_step + pm_sub : e / LG]) && (!wm || wm[e]);
                 const float w = on ? ex2_approx(fmaf(__ldg(wl + e), kLog2e, -mlog)) * inv : 0.f;
                 p.grad_logits[ba * nE + e] = -w * S;
             }

@@ -15,7 +15,9 @@ for what in "$@"; do
   fi
 done
 for v in $variants; do
-  if [ $v = default ]; then unset GF_B200_LIB; else export GF_B200_LIB=$PWD/gaussianformer_b200/csrc/variants/libgf_b200_$v.so; fi
+  unset GF_B200_LIB GF_B200_SPLIT
+  if [ $v = nosplit ]; then export GF_B200_SPLIT=0;
+  elif [ $v != default ]; then export GF_B200_LIB=$PWD/gaussianformer_b200/csrc/variants/libgf_b200_$v.so; fi
   if [ $v != default ]; then
     timeout 600 python -m pytest tests/test_splat_gpu.py tests/test_cabi_gpu.py -m gpu -x -q 2>&1 | tail -1 | sed "s/^/$v parity: /"
   fi
@@ -31,7 +33,7 @@ except Exception as e:
 PY
   done
 done
-unset GF_B200_LIB
+unset GF_B200_LIB GF_B200_SPLIT
 for what in "$@"; do
   if [ $what = ncu ]; then
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \

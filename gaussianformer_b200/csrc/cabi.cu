@@ -78,15 +78,6 @@ static int num_sms_of_current_device(int *out) {
     return GF_OK;
 }
 
-int sms_for_planning() {
-    int n = 0;
-    if (num_sms_of_current_device(&n) != GF_OK || n <= 0) {
-        cudaGetLastError();   // no usable device (size queries on a CPU box): plan for a nominal B200
-        return 148;
-    }
-    return n;
-}
-
 static int check_desc(const gf_splat_desc *d) {
     GF_REQUIRE(d != nullptr, GF_ERR_INVALID_ARG, "splat: desc is NULL");
     GF_REQUIRE(d->G >= 0 && d->N >= 0, GF_ERR_INVALID_ARG, "splat: negative G or N");

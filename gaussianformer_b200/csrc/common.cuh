@@ -59,24 +59,12 @@ struct SplatWorkspace {
     uint32_t *masks;       // [nsuper, nwords] bit g of supertile s: box(g) overlaps s
     int32_t *lists;        // [nsuper, G] ascending Gaussian indices per supertile
     int32_t *counts;       // [nsuper]
-    uint32_t *split_counters;  // [split_rem] arrival counters of the K-split tail bins (zeroed by list_kernel)
-    float *split_scratch;      // [split_rem * split_S] partial accumulator tiles of those bins
-    int split_main, split_rem, split_S;   // plan_render_split(): bins [0, main) whole, the last `rem` bins in S list parts
     int st;                // supertile edge (columns)
     int nsx, nsy, nsuper;  // supertile grid
     int nwords;            // ceil(G/32)
     int pack_ctas;
     size_t bytes;
 };
-
-// The render grid of the base variant is nbins CTAs on slots = SMs x GF_RENDER_CTAS resident CTAs.  When the last
-// round would be a small remainder (nuScenes: 1250 bins on 592 slots = 2 full rounds + 66 CTAs that keep 66 SMs busy
-// for a third whole round while 82 idle -- measured: 31 % of the kernel's time), the remainder bins are split along
-// their Gaussian list into S parts, one CTA each, whose partial sums are added in part order by the last one to
-// finish (deterministic; splat_forward.cu).  Returns S = 1 when splitting does not pay.
-void plan_render_split(const gf_splat_desc &d, int num_sms, int *main_bins, int *rem_bins, int *parts);
-int sms_for_planning();   // SM count of the current device (cached); a nominal 148 when no device is usable
-constexpr int kMaxSplitParts = 8;
 
 constexpr int kPackThreads = 64;   // small CTAs: ~400 of them cover the 148 SMs several times over
 

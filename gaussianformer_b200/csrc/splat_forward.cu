@@ -36,11 +36,7 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
     const int H = p.d.H, W = p.d.W, D = p.d.D;
 
     // ---- which voxels are mine -------------------------------------------------------------------
-    // CTA id -> (bin, list part): ids below split_main own a whole bin; the rest come in groups of split_S CTAs that
-    // share one of the last bins (bins are numbered z chunk fastest, then y, then x)
-    int bin = blockIdx.x;
-    if (static_cast<int>(blockIdx.x) >= p.split_main) bin = p.split_main + (blockIdx.x - p.split_main) / p.split_S;
-    const int binZ0 = (bin % p.nzc) * kBinZ, binY0 = ((bin / p.nzc) % p.nby) * kBinY, binX0 = (bin / (p.nzc * p.nby)) * kBinX;
+    const int binX0 = blockIdx.z * kBinX, binY0 = blockIdx.y * kBinY, binZ0 = blockIdx.x * kBinZ;
 #if GF_TILE_MAP == 1
     const int lx = lane & 7, ly = lane >> 3, lq = warp;                                                    // z group
 #else
@@ -210,47 +206,7 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
             }
         }
     };
-    {
-        const bool split = static_cast<int>(blockIdx.x) >= p.split_main;
-        walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, split ? (blockIdx.x - p.split_main) % p.split_S : 0,
-                          split ? p.split_S : 1, stage_e, stage_acc);
-    }
-
-    // ---- K-split bins: the parts leave their partial sums in scratch; the last one to arrive adds them in part order
-    //      (so the result does not depend on which CTA that is) and carries on to the epilogue -------------------------
-    if (!PROB && static_cast<int>(blockIdx.x) >= p.split_main) {   // (recomputed from blockIdx: nothing kept live across the walk)
-        constexpr int NT = 512 / VOX;
-        constexpr int NV4 = VOX * CP2 / 2;    // float4 words per thread (VOX * CP2 float2 accumulators)
-        static_assert((VOX * CP2) % 2 == 0, "accumulators pair up into float4 words");
-        const int nparts = p.split_S;
-        const int tail = (blockIdx.x - p.split_main) / nparts, part = (blockIdx.x - p.split_main) % nparts;
-        float4 *mine = reinterpret_cast<float4 *>(p.split_scratch) + (static_cast<size_t>(tail) * nparts + part) * NV4 * NT + tid;
-#pragma unroll
-        for (int i = 0; i < NV4; ++i) {
-            const float2 a = acc[(2 * i) / CP2][(2 * i) % CP2], b = acc[(2 * i + 1) / CP2][(2 * i + 1) % CP2];
-            __stcg(mine + static_cast<size_t>(i) * NT, make_float4(a.x, a.y, b.x, b.y));
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) sm.split_last = atomicAdd(p.split_counters + tail, 1u) == static_cast<uint32_t>(nparts - 1) ? 1 : 0;
-        __syncthreads();
-        if (!sm.split_last) return;
-        __threadfence();
-#pragma unroll
-        for (int v = 0; v < VOX; ++v)
-#pragma unroll
-            for (int c = 0; c < CP2; ++c) acc[v][c] = make_float2(0.f, 0.f);
-        const float4 *all = reinterpret_cast<const float4 *>(p.split_scratch) + static_cast<size_t>(tail) * nparts * NV4 * NT + tid;
-        for (int q = 0; q < nparts; ++q) {
-#pragma unroll
-            for (int i = 0; i < NV4; ++i) {
-                const float4 t4 = __ldcg(all + (static_cast<size_t>(q) * NV4 + i) * NT);
-                float2 &a = acc[(2 * i) / CP2][(2 * i) % CP2];
-                float2 &b = acc[(2 * i + 1) / CP2][(2 * i + 1) % CP2];
-                a.x += t4.x; a.y += t4.y; b.x += t4.z; b.y += t4.w;
-            }
-        }
-    }
+    walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, stage_e, stage_acc);
 
     // ---- epilogue ----------------------------------------------------------------------------------
     if (!(col_ok && Z0 < D)) return;
@@ -347,35 +303,6 @@ int launch_render_tc(const RenderParams &rp, cudaStream_t stream);  // splat_for
 // Two tile kernels exist for canonical-order points.  The SIMT quad kernel (this file) is the default
 // because it is the faster one on B200 today (profiles/README.md); GF_B200_RENDER=tc selects the
 // tcgen05 kernel (splat_forward_tc.cu), kept for A/B measurements.  Both evaluate stray points inline.
-// GF_B200_SPLIT=0 switches the K-split of the last bins off (A/B measurements)
-static bool render_split_enabled() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char *e = getenv("GF_B200_SPLIT");
-        cached = (e && e[0] == '0') ? 0 : 1;
-    }
-    return cached == 1;
-}
-
-void plan_render_split(const gf_splat_desc &d, int num_sms, int *main_bins, int *rem_bins, int *parts) {
-    const long long nbins = static_cast<long long>((d.H + kBinX - 1) / kBinX) * ((d.W + kBinY - 1) / kBinY) *
-                            ((d.D + kBinZ - 1) / kBinZ);
-    const long long slots = static_cast<long long>(num_sms) * GF_RENDER_CTAS;
-    *main_bins = static_cast<int>(nbins);
-    *rem_bins = 0;
-    *parts = 1;
-    const bool tile_shape = static_cast<long long>(d.N) == static_cast<long long>(d.H) * d.W * d.D;
-    if (d.variant != GF_SPLAT_BASE || !tile_shape || slots <= 0 || nbins <= slots) return;
-    const long long rem = nbins % slots;
-    if (rem == 0 || 2 * rem > slots) return;            // the last round is (nearly) full anyway
-    long long S = slots / rem;
-    if (S > kMaxSplitParts) S = kMaxSplitParts;
-    if (S < 2) return;
-    *main_bins = static_cast<int>(nbins - rem);
-    *rem_bins = static_cast<int>(rem);
-    *parts = static_cast<int>(S);
-}
-
 static bool use_simt_render() {
     static int cached = -1;
     if (cached < 0) {
@@ -402,19 +329,8 @@ static int launch_render_t(const RenderParams &rp, bool tile_path, int num_sms, 
     if (tile_path && !use_simt_render()) return launch_render_tc(rp, stream);
     if (tile_path) {
         const int nbx = (rp.d.H + kBinX - 1) / kBinX;
-        const long long nbins = static_cast<long long>(rp.nzc) * rp.nby * nbx;
-        // 1-D grid: split_main whole bins, then split_S CTAs for each of the remaining bins (RenderParams)
-        long long nctas = nbins;
-        RenderParams rq = rp;
-        if (PROB || rq.split_S <= 1 || !render_split_enabled()) {
-            rq.split_main = static_cast<int>(nbins);
-            rq.split_S = 1;
-        } else {
-            nctas = rq.split_main + (nbins - rq.split_main) * rq.split_S;
-        }
-        GF_REQUIRE(nctas < (1ll << 31), GF_ERR_UNSUPPORTED, "splat: grid too large for the render launch");
-        const dim3 grid(static_cast<unsigned>(nctas));
-        const RenderParams &rp = rq;   // (shadows the argument for the launches below)
+        GF_REQUIRE(rp.nby <= 65535 && nbx <= 65535, GF_ERR_UNSUPPORTED, "splat: grid too large for the render launch");
+        const dim3 grid(rp.nzc, rp.nby, nbx);
         if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_before, stream));
 #ifdef GF_ENABLE_VOX2   // experiment kept in the source: 2 voxels per thread (measured equal to 4 on B200)
         if (render_vox() == 2)
@@ -456,10 +372,6 @@ int launch_render(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_sp
     rp.nsy = ws.nsy;
     rp.nby = (d.W + kBinY - 1) / kBinY;
     rp.nzc = (d.D + kBinZ - 1) / kBinZ;
-    rp.split_main = ws.split_main;
-    rp.split_S = ws.split_S;
-    rp.split_scratch = ws.split_scratch;
-    rp.split_counters = ws.split_counters;
     const bool prob = d.variant == GF_SPLAT_PROB;
 #define GF_CASE(CC)                                                                  \
     case CC:                                                                         \

@@ -150,8 +150,6 @@ struct ListParams {
     int G;
     int pack_ctas;
     uint32_t initial_flags;
-    uint32_t *split_counters;   // zeroed here for the render kernel's K-split tail bins
-    int n_split;
 };
 
 constexpr int kListThreads = 256;
@@ -159,8 +157,6 @@ constexpr int kListWordsPerThread = 4;   // consecutive mask words per thread an
 
 __global__ void __launch_bounds__(kListThreads) list_kernel(const ListParams p) {
     const int s = blockIdx.x;
-    if (s == 0)
-        for (int i = threadIdx.x; i < p.n_split; i += kListThreads) p.split_counters[i] = 0u;
     const uint32_t *words = p.masks + static_cast<size_t>(s) * p.nwords;
     int32_t *list = p.lists + static_cast<size_t>(s) * p.G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -259,10 +255,6 @@ int plan_forward_workspace(const gf_splat_desc &d, void *base, SplatWorkspace *w
     ws->masks = reinterpret_cast<uint32_t *>(take(size_t(ws->nsuper) * ws->nwords * 4));
     ws->lists = reinterpret_cast<int32_t *>(take(size_t(ws->nsuper) * d.G * 4));
     ws->counts = reinterpret_cast<int32_t *>(take(size_t(ws->nsuper) * 4));
-    plan_render_split(d, sms_for_planning(), &ws->split_main, &ws->split_rem, &ws->split_S);
-    const size_t tile_floats = size_t(kRenderThreads) * kVox * 2 * ((d.C + 1) / 2);   // one CTA's accumulators
-    ws->split_counters = reinterpret_cast<uint32_t *>(take(size_t(ws->split_rem > 0 ? ws->split_rem : 1) * 4));
-    ws->split_scratch = reinterpret_cast<float *>(take(ws->split_S > 1 ? size_t(ws->split_rem) * ws->split_S * tile_floats * 4 : 0));
     ws->bytes = off;
     return GF_OK;
 }
@@ -295,8 +287,6 @@ int launch_prep(const gf_splat_desc &d, const gf_splat_inputs &in, const SplatWo
     lp.G = d.G;
     lp.pack_ctas = ws.pack_ctas;
     lp.initial_flags = initial_flags;
-    lp.split_counters = ws.split_counters;
-    lp.n_split = ws.split_S > 1 ? ws.split_rem : 0;
     GF_CUDA_TRY(launch_chained(list_kernel, dim3(ws.nsuper), dim3(kListThreads), 0, stream, lp));
     return GF_OK;
 }

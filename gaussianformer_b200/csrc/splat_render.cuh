@@ -19,10 +19,6 @@ struct RenderParams {
     int st, nsy;     // supertile edge, supertiles along y
     int nby;         // bins along y
     int nzc;         // z chunks
-    // K-split of the last bins (plan_render_split, common.cuh): CTA ids >= split_main come in groups of split_S
-    int split_main, split_S;
-    float *split_scratch;
-    uint32_t *split_counters;
 };
 
 // index of the largest of C values, lowest index on ties

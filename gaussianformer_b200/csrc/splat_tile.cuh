@@ -48,7 +48,6 @@ struct RenderSmem {
     alignas(8) uint64_t bar_full[kRing];       // records of the slot have landed (one cp.async arrival per thread)
     alignas(8) uint64_t bar_empty[kRing];      // every warp is done with the slot (one arrival per warp)
     int warp_count[2][NT / 32];
-    int split_last;                            // K-split: this CTA is the last of its bin to finish
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -94,8 +93,7 @@ struct RecView {
 // once per touching record, and every step does useful work in every lane that still has hits.
 template <int C, int VOX, class StageE, class StageAcc>
 __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, VOX> &sm, int binX0, int binY0, int binZ0,
-                                          uint32_t my_xy, int my_zshift, int part, int nparts, StageE &&stage_e,
-                                          StageAcc &&stage_acc) {
+                                          uint32_t my_xy, int my_zshift, StageE &&stage_e, StageAcc &&stage_acc) {
     constexpr int REC = rec_floats(C);
     constexpr int NT = 512 / VOX, NWARP = NT / 32;
     constexpr uint32_t VMASK = (1u << VOX) - 1u;
@@ -116,14 +114,11 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
     // ---- candidates: the ascending list of this bin's supertile ------------------------------------
     const int st_shift = 31 - __clz(p.st);
     const int s = (binX0 >> st_shift) * p.nsy + (binY0 >> st_shift);
-    // part `part` of `nparts` walks its contiguous share of the supertile's ascending candidate list (K-split of the
-    // last bins, common.cuh: plan_render_split); nparts = 1 is the whole list
-    const long long ncand_all = p.counts[s];
-    const int ncand = static_cast<int>(ncand_all * (part + 1) / nparts);
+    const int ncand = p.counts[s];
     const int32_t *cand = p.lists + static_cast<size_t>(s) * p.d.G;
     const uint32_t bX1 = min(binX0 + kBinX, H) - 1, bY1 = min(binY0 + kBinY, W) - 1, bZ1 = min(binZ0 + kBinZ, D) - 1;
 
-    int cpos = static_cast<int>(ncand_all * part / nparts);
+    int cpos = 0;
     while (cpos < ncand) {
         __syncthreads();   // previous segment fully consumed (and, the first time, barriers initialised)
         // ======================= Phase A: ordered survivors of the box test ==========================

@@ -17,6 +17,7 @@ done
 for v in $variants; do
   unset GF_B200_LIB GF_B200_SPLIT
   if [ $v = nosplit ]; then export GF_B200_SPLIT=0;
+  elif [ ${v:0:5} = split ]; then export GF_B200_SPLIT=${v:5};
   elif [ $v != default ]; then export GF_B200_LIB=$PWD/gaussianformer_b200/csrc/variants/libgf_b200_$v.so; fi
   if [ $v != default ]; then
     timeout 600 python -m pytest tests/test_splat_gpu.py tests/test_cabi_gpu.py -m gpu -x -q 2>&1 | tail -1 | sed "s/^/$v parity: /"

@@ -76,13 +76,6 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
                     pz[v] = __ldg(p.pts + 3 * (n0 + v) + 2);
                 }
         }
-    }
-    // Everything above depends on the caller's inputs only; the records, boxes, lists and the status word come from the
-    // two preparation kernels, which this grid may have been launched ahead of.  The first round of the bin's
-    // candidates is requested now, before the points are consumed (tile_prefetch, splat_tile.cuh).
-    pdl_wait();
-    const TilePrefetch pf = tile_prefetch<VOX>(p, binX0, binY0);
-    if (col_ok && Z0 < D) {
         // canonical-order check: point n must lie in voxel n.  A cheap reciprocal estimate settles every
         // point that is not within 1e-3 cells of a voxel face; only those pay the exact IEEE divisions.
         const float inv = __frcp_rn(p.d.grid_size);
@@ -127,6 +120,9 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
         zsum[v] = 0.f; dens[v] = 0.f; keep[v] = 1.f;
     }
 
+    // Everything above depends on the caller's inputs only; the records, boxes, lists and the status word
+    // come from the two preparation kernels, which this grid may have been launched ahead of.
+    pdl_wait();
     if (stray) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
     // One step of a lane = one (record, my VOX voxels) evaluation, in two stages so that the walker can overlap the
     // loads of the next step with the arithmetic of the current one:
@@ -210,7 +206,7 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
             }
         }
     };
-    walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, pf, stage_e, stage_acc);
+    walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, stage_e, stage_acc);
 
     // ---- epilogue ----------------------------------------------------------------------------------
     if (!(col_ok && Z0 < D)) return;

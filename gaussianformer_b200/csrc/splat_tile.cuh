@@ -75,37 +75,6 @@ struct RecView {
     }
 };
 
-// First round of Phase A, requested early: the candidate indices of the bin's supertile are read BEFORE the list
-// length is known (every supertile owns room for G entries, so the read is in bounds; entries past the length are
-// discarded), the length in parallel, the candidates' boxes as soon as both are there.  The render kernel issues
-// this before it consumes its points, so a CTA's start-up is max(points, length | candidates -> boxes) instead of
-// points -> length -> candidates -> boxes (a CTA's life is dominated by this latency chain).
-constexpr int kPre = 4;   // rounds of NT candidates fetched together (memory-level parallelism)
-struct TilePrefetch {
-    int ncand;
-    int gg[kPre];
-    uint4 bb[kPre];
-};
-template <int VOX>
-__device__ __forceinline__ TilePrefetch tile_prefetch(const RenderParams &p, int binX0, int binY0) {
-    constexpr int NT = 512 / VOX;
-    const int tid = threadIdx.x;
-    const int st_shift = 31 - __clz(p.st);
-    const int s = (binX0 >> st_shift) * p.nsy + (binY0 >> st_shift);
-    const int32_t *cand = p.lists + static_cast<size_t>(s) * p.d.G;
-    TilePrefetch f;
-    int raw[kPre];
-#pragma unroll
-    for (int u = 0; u < kPre; ++u) raw[u] = (u * NT + tid < p.d.G) ? __ldg(cand + u * NT + tid) : -1;
-    f.ncand = __ldg(p.counts + s);
-#pragma unroll
-    for (int u = 0; u < kPre; ++u) f.gg[u] = (u * NT + tid < f.ncand) ? raw[u] : -1;
-#pragma unroll
-    for (int u = 0; u < kPre; ++u)
-        f.bb[u] = f.gg[u] >= 0 ? __ldg(reinterpret_cast<const uint4 *>(p.boxes) + f.gg[u]) : make_uint4(1u, 1u, 1u, 1u);
-    return f;
-}
-
 // The caller supplies the two stages of a lane's step:
 //   stage_e(float4 g0, float4 g1, float4 g2, RecView record, uint32_t zbits, bool active)   geometry chunks 0..2 (already
 //       loaded) -> weights; `active` says whether this lane has a record to evaluate in this step (its column lies
@@ -124,8 +93,7 @@ __device__ __forceinline__ TilePrefetch tile_prefetch(const RenderParams &p, int
 // once per touching record, and every step does useful work in every lane that still has hits.
 template <int C, int VOX, class StageE, class StageAcc>
 __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, VOX> &sm, int binX0, int binY0, int binZ0,
-                                          uint32_t my_xy, int my_zshift, const TilePrefetch &pf, StageE &&stage_e,
-                                          StageAcc &&stage_acc) {
+                                          uint32_t my_xy, int my_zshift, StageE &&stage_e, StageAcc &&stage_acc) {
     constexpr int REC = rec_floats(C);
     constexpr int NT = 512 / VOX, NWARP = NT / 32;
     constexpr uint32_t VMASK = (1u << VOX) - 1u;
@@ -146,7 +114,7 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
     // ---- candidates: the ascending list of this bin's supertile ------------------------------------
     const int st_shift = 31 - __clz(p.st);
     const int s = (binX0 >> st_shift) * p.nsy + (binY0 >> st_shift);
-    const int ncand = pf.ncand;
+    const int ncand = p.counts[s];
     const int32_t *cand = p.lists + static_cast<size_t>(s) * p.d.G;
     const uint32_t bX1 = min(binX0 + kBinX, H) - 1, bY1 = min(binY0 + kBinY, W) - 1, bZ1 = min(binZ0 + kBinZ, D) - 1;
 
@@ -156,21 +124,17 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
         // ======================= Phase A: ordered survivors of the box test ==========================
         int nlist = 0;
         while (cpos < ncand && nlist + NT <= kQuadSeg) {
+            constexpr int kPre = 4;   // rounds fetched together (memory-level parallelism)
             int gg[kPre];
             uint4 bb[kPre];
-            if (cpos == 0) {   // the first rounds were requested by tile_prefetch()
 #pragma unroll
-                for (int u = 0; u < kPre; ++u) { gg[u] = pf.gg[u]; bb[u] = pf.bb[u]; }
-            } else {
-#pragma unroll
-                for (int u = 0; u < kPre; ++u) {
-                    const int i = cpos + u * NT + tid;
-                    gg[u] = i < ncand ? __ldg(cand + i) : -1;
-                }
-#pragma unroll
-                for (int u = 0; u < kPre; ++u)
-                    bb[u] = gg[u] >= 0 ? __ldg(reinterpret_cast<const uint4 *>(p.boxes) + gg[u]) : make_uint4(1u, 1u, 1u, 1u);
+            for (int u = 0; u < kPre; ++u) {
+                const int i = cpos + u * NT + tid;
+                gg[u] = i < ncand ? __ldg(cand + i) : -1;
             }
+#pragma unroll
+            for (int u = 0; u < kPre; ++u)
+                bb[u] = gg[u] >= 0 ? __ldg(reinterpret_cast<const uint4 *>(p.boxes) + gg[u]) : make_uint4(1u, 1u, 1u, 1u);
 #pragma unroll
             for (int u = 0; u < kPre; ++u) {
                 if (cpos >= ncand || nlist + NT > kQuadSeg) break;   // uniform

@@ -115,8 +115,13 @@ def _cpu_port_once(kw, inp):
     pi, mi, radii = oracle.host_prep(a["pts"], a["means"], a["scales"], kw["pc_min"], kw["grid_size"],
                                      kw["scale_multiplier"])
     cov6 = oracle.cov6_from_3x3(a["cov"])
-    oracle.splat_forward(a["pts"], pi, a["means"], mi, a["opa"], a["sem"], cov6, radii, dims, "f32")
-    return time.perf_counter() - t0
+    out, pairs = oracle.splat_forward(a["pts"], pi, a["means"], mi, a["opa"], a["sem"], cov6, radii, dims, "f32")
+    sec = time.perf_counter() - t0
+    _LAST_PORT["logits"], _LAST_PORT["pairs"] = out, int(pairs)
+    return sec
+
+
+_LAST_PORT = {}   # logits / (voxel, Gaussian) pair count of the most recent CPU-port forward (checker side figures)
 
 
 def run_reference_arm(args):
@@ -340,6 +345,23 @@ def main():
         sec = sum(reps) / len(reps)
         cpu_baseline = {"value": G_COUNTED / sec, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
                         "sample": f"3 full forward passes of the {WORKLOAD} sample, {sec:.3f} s each (C/OpenMP oracle)"}
+        try:
+            # secondary, work-normalised figure: in-box (voxel, Gaussian) pairs per second and the fp32
+            # rate they stand for at ~56 flop + 1 exp per pair; and the headline sample checked against the CPU port
+            pairs = _LAST_PORT["pairs"]
+            extras["work"] = {"pairs": pairs, "pairs_per_s": pairs / (render_ms * 1e-3), "flop_per_pair": 56,
+                              "fp32_tflops": 56 * pairs / (render_ms * 1e-3) / 1e12,
+                              "what": "in-box (voxel, Gaussian) pairs of the sample over the render kernel's time"}
+            got = outs[0].float().cpu().numpy()
+            want = _LAST_PORT["logits"]
+            import numpy as np
+            err = np.abs(got - want)
+            extras["parity_vs_cpu_port"] = {
+                "max_abs_err": float(err.max()), "max_rel_err_above_1e-3": float((err / np.maximum(np.abs(want), 1e-3)).max()),
+                "argmax_differences": int((got.argmax(1) != want.argmax(1)).sum()), "voxels": int(got.shape[0]),
+                "what": "logits of the timed sample (resident set 0) vs the fp32 C/OpenMP oracle on the host"}
+        except Exception as e:
+            extras["parity_error"] = repr(e)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -407,6 +429,21 @@ def side_measurements(dev, kw, inp0, resident, desc):
         ml.validate = False
         tl = {k: v.to(dev) for k, v in inpl.items()}
         out["gs144000_fwd_ms"] = timeit(lambda: ml(tl["pts"], tl["means"], tl["opa"], tl["sem"], tl["scales"], tl["cov"]), reps=10)
+        try:
+            # north star: mIoU unchanged (SURVEY.md 8d recipe on the 144 000-Gaussian sample, whose arg-max spreads over
+            # all 18 classes): fused arg-max of the CUDA path vs the CPU port's arg-max, scored with the reference's MeanIoU
+            from gaussianformer_b200.metric import miou_parity, synthetic_labels
+            _lg, occ = ml.forward_with_occupancy(tl["pts"], tl["means"], tl["opa"], tl["sem"], tl["scales"], tl["cov"])
+            _cpu_port_once(kwl, inpl)
+            want = _LAST_PORT["logits"]
+            labels, mask = synthetic_labels(want, want.shape[1])
+            r = miou_parity(occ.cpu(), want.argmax(1), labels, mask, want.shape[1])
+            out["miou_parity_gs144000"] = {
+                "miou_cuda": r["new"][0], "miou_cpu_port": r["ref"][0], "abs_diff": r["abs_diff"],
+                "argmax_differences": int((occ.cpu().numpy().astype("int64") != want.argmax(1)).sum()),
+                "voxels": int(want.shape[0])}
+        except Exception as e:
+            out["miou_parity_error"] = repr(e)
         del tl
         fms, loc, w = make_daf_inputs(seed=0)
         feat, shape, start = DAF.feature_maps_format([f.to(dev) for f in fms])

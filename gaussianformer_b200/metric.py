@@ -49,3 +49,28 @@ class MeanIoU:
                 ious.append(float(correct[i] / (seen[i] + positive[i] - correct[i])))
         occ = float(correct[-1] / (seen[-1] + positive[-1] - correct[-1]))
         return sum(ious) / len(ious) * 100.0, occ * 100.0
+
+
+def synthetic_labels(oracle_logits, num_classes, flip_fraction=0.1, seed=1):
+    """labels = arg-max of the oracle's logits with ``flip_fraction`` of the voxels re-drawn
+    uniformly from ``0..num_classes-1`` (seeded); mask = ``label != 0`` (dataset/transform_3d.py:509)."""
+    logits = torch.as_tensor(oracle_logits)
+    labels = logits.argmax(dim=1)
+    gen = torch.Generator().manual_seed(seed)
+    flip = torch.rand(labels.shape[0], generator=gen) < flip_fraction
+    labels = torch.where(flip, torch.randint(0, num_classes, labels.shape, generator=gen), labels)
+    return labels, labels != 0
+
+
+def miou_parity(pred_new, pred_ref, labels, mask, num_classes, empty_label=None):
+    """mIoU / occupancy IoU of two arg-max predictions against the same labels, as the reference evaluates them
+    (``misc/metric_util.py:35-111``: classes 1..C-2 scored, class C-1 = empty).  Returns
+    ``{"new": (miou, iou), "ref": (miou, iou), "abs_diff": max |difference| in mIoU points}``."""
+    empty_label = num_classes - 1 if empty_label is None else empty_label
+    out = {}
+    for name, pred in (("new", pred_new), ("ref", pred_ref)):
+        m = MeanIoU(list(range(1, num_classes - 1)), empty_label=empty_label)
+        m.after_step(torch.as_tensor(pred).long().cpu(), labels, mask)
+        out[name] = m.after_epoch()
+    out["abs_diff"] = max(abs(out["new"][0] - out["ref"][0]), abs(out["new"][1] - out["ref"][1]))
+    return out

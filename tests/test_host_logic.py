@@ -80,3 +80,25 @@ def test_mean_iou_definition():
     assert abs(miou - 100 / 3) < 1e-9
     # occupancy: seen 4 (gt != 0), positive 4, correct 3 -> 3/5
     assert abs(iou - 60.0) < 1e-9
+
+
+def test_miou_parity_recipe_on_the_oracle():
+    """SURVEY.md 8(d) mIoU parity recipe, exercised on the CPU: fp32 vs fp64 oracle logits of the tiny config give
+    the same mIoU against the seeded noisy labels up to the voxels whose top two classes tie numerically (each such
+    flip moves a class IoU of this 10 000-voxel grid by ~1e-3; at the full 640 000-voxel shape bench.py reports the
+    figure); a deliberately damaged prediction does not."""
+    import numpy as np
+    import helpers as h
+    from gaussianformer_b200.metric import miou_parity, synthetic_labels
+    kw, inp, variant = h.splat_case("tiny", 0, False)
+    ref64 = h.oracle_forward(kw, inp, variant, precision="f64")["logits"]
+    ref32 = h.oracle_forward(kw, inp, variant, precision="f32")["logits"]
+    C = ref64.shape[1]
+    labels, mask = synthetic_labels(ref64, C)
+    assert 0.05 < float((labels != torch.as_tensor(ref64).argmax(1)).float().mean()) < 0.15
+    r = miou_parity(ref32.argmax(1), ref64.argmax(1), labels, mask, C)
+    flips = int((ref32.argmax(1) != ref64.argmax(1)).sum())
+    assert flips <= 20 and r["abs_diff"] <= 0.01 * max(flips, 1) and r["ref"][0] > 50.0
+    bad = ref64.argmax(1).copy()
+    bad[: bad.shape[0] // 4] = 3
+    assert miou_parity(bad, ref64.argmax(1), labels, mask, C)["abs_diff"] > 1.0

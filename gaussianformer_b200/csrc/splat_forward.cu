@@ -128,6 +128,75 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
     // loads of the next step with the arithmetic of the current one:
     //   stage_e    exponent and weight of my voxels from the record's geometry chunks; starts the loads of its class chunks
     //   stage_acc  the class accumulation (VOX x C/2 packed FMAs) with the weights / class chunks of the last stage_e
+#if GF_TILE_PIPE == 2
+    // Branch-free fused step (splat_tile.cuh): weights of the CURRENT hit in wv[], its record in cur_rec.
+    float wv[VOX];
+    RecView cur_rec;
+    cur_rec.addr = 0;
+    // exponent + weights of one hit, no branches: COLUMN is decided once per CTA (every thread's points share x, y)
+    auto weights_of = [&](auto column_tag, const RecView rec, uint32_t zb, float (&w)[VOX]) {
+        constexpr bool COLUMN = decltype(column_tag)::value;
+        const float4 g0 = rec.chunk(0), g1 = rec.chunk(1), g2c = rec.chunk(2);
+        if constexpr (COLUMN) {
+            const float dx = g0.x - px[0], dy = g0.y - py[0];
+            float t1 = g1.x * dx;
+            t1 = fmaf(g1.w, dy, t1);
+            float A = t1 * dx;
+            A = fmaf(g1.y * dy, dy, A);
+            const float B = fmaf(g2c.x, dy, g2c.y * dx);
+#pragma unroll
+            for (int v = 0; v < VOX; ++v) {
+                const float dz = g0.z - pz[v];
+                const float q = fmaf(fmaf(g1.z, dz, B), dz, A);
+                const float E = ((zb >> v) & 1u) ? ex2_approx(q) : 0.f;
+                w[v] = PROB ? g0.w * E : E;
+                if (PROB) { zsum[v] += w[v]; dens[v] += E; keep[v] *= (1.f - E); }
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < VOX; ++v) {
+                const float dx = g0.x - px[v], dy = g0.y - py[v], dz = g0.z - pz[v];
+                float t1 = g1.x * dx;
+                t1 = fmaf(g1.w, dy, t1);
+                t1 = fmaf(g2c.y, dz, t1);
+                float t2 = g1.y * dy;
+                t2 = fmaf(g2c.x, dz, t2);
+                float q = t1 * dx;
+                q = fmaf(t2, dy, q);
+                q = fmaf(g1.z * dz, dz, q);
+                const float E = ((zb >> v) & 1u) ? ex2_approx(q) : 0.f;
+                w[v] = PROB ? g0.w * E : E;
+                if (PROB) { zsum[v] += w[v]; dens[v] += E; keep[v] *= (1.f - E); }
+            }
+        }
+    };
+    auto run_walk = [&](auto column_tag) {
+        auto prime = [&](const RecView rec, uint32_t zb, bool) {
+            weights_of(column_tag, rec, zb, wv);
+            cur_rec = rec;
+        };
+        auto fused = [&](const RecView next, uint32_t zb_next, bool) {
+            float wn[VOX];
+            weights_of(column_tag, next, zb_next, wn);          // same basic block as the accumulation below
+#pragma unroll
+            for (int c4 = 0; c4 < (C + 3) / 4; ++c4) {
+                const float4 s4 = cur_rec.chunk(3 + c4);
+#pragma unroll
+                for (int v = 0; v < VOX; ++v) {
+                    const float2 ww = make_float2(wv[v], wv[v]);
+                    acc[v][2 * c4] = __ffma2_rn(make_float2(s4.x, s4.y), ww, acc[v][2 * c4]);
+                    if (2 * c4 + 1 < CP2) acc[v][2 * c4 + 1] = __ffma2_rn(make_float2(s4.z, s4.w), ww, acc[v][2 * c4 + 1]);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VOX; ++v) wv[v] = wn[v];
+            cur_rec = next;
+        };
+        walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, prime, fused);
+    };
+    if (__syncthreads_and(column ? 1 : 0)) run_walk(std::true_type{});
+    else run_walk(std::false_type{});
+#else
     float wv[VOX];
 #if GF_TILE_PIPE
     float4 cls[(C + 3) / 4];
@@ -207,6 +276,8 @@ __global__ void __launch_bounds__(512 / VOX, VOX == 4 ? (PROB ? 3 : GF_RENDER_CT
         }
     };
     walk_tile<C, VOX>(p, sm, binX0, binY0, binZ0, my_xy, my_zshift, stage_e, stage_acc);
+
+#endif
 
     // ---- epilogue ----------------------------------------------------------------------------------
     if (!(col_ok && Z0 < D)) return;

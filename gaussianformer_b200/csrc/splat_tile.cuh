@@ -48,6 +48,9 @@ struct RenderSmem {
     alignas(8) uint64_t bar_full[kRing];       // records of the slot have landed (one cp.async arrival per thread)
     alignas(8) uint64_t bar_empty[kRing];      // every warp is done with the slot (one arrival per warp)
     int warp_count[2][NT / 32];
+#if GF_TILE_PIPE == 2
+    alignas(128) float zero_row[32];           // the "record" of a lane without a hit: weights 0, classes 0
+#endif
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -81,6 +84,12 @@ struct RecView {
 //       inside the Gaussian's box and at least one of its voxels does); bit v of zbits whether its voxel v does.
 //       Inactive lanes must not touch `record`.
 //   stage_acc(bool active)   accumulate with what the last stage_e left behind.
+// GF_TILE_PIPE = 2 (unmeasured, prepared for the next round): branch-free fused step.  The two callables become
+//   prime(RecView, zbits, active)            evaluate a lane's first hit of the batch (weights only)
+//   fused(RecView next, zbits, active_next)  accumulate the CURRENT hit and evaluate the NEXT one in ONE basic block,
+// so that the compiler can interleave the 36 independent FFMA2 of the accumulation with the dependent chain
+// (shared load -> quadratic form -> ex2) of the next exponent.  A lane without a hit points at an all-zero row
+// (weights 0, classes 0) instead of branching, so no lane ever multiplies a record it is not entitled to.
 // GF_TILE_PIPE = 1 software-pipelines the two: the geometry of a lane's NEXT hit is requested before stage_acc of the
 // current one, so its shared-memory latency hides behind the accumulation instead of stalling the next exponent.
 //
@@ -108,6 +117,9 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
         }
         mbar_fence_init();
     }
+#if GF_TILE_PIPE == 2
+    if (tid < 32) sm.zero_row[tid] = 0.f;   // published by the first __syncthreads of Phase A
+#endif
     uint32_t gb = 0;   // batches consumed so far by this CTA: drives ring slots and barrier parities
     // (the __syncthreads of Phase A below publishes the barrier initialisation)
 
@@ -248,7 +260,24 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C, V
                 zb = (e >> my_zshift) & VMASK;
             };
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#if GF_TILE_PIPE
+#if GF_TILE_PIPE == 2
+            {
+                const uint32_t zero_addr = smem_u32(&sm.zero_row[0]);
+                bool act_c, act_n;
+                RecView rv;
+                uint32_t zb;
+                next_hit(act_c, rv, zb);
+                if (!act_c) { rv.addr = zero_addr; zb = 0u; }
+                stage_e(rv, zb, act_c);                       // prime
+                while (__any_sync(0xffffffffu, act_c)) {
+                    next_hit(act_n, rv, zb);
+                    if (!act_n) { rv.addr = zero_addr; zb = 0u; }
+                    stage_acc(rv, zb, act_n);                 // fused: accumulate current, evaluate next
+                    act_c = act_n;
+                }
+                (void)zero4;
+            }
+#elif GF_TILE_PIPE
             bool act_c, act_n;
             RecView rv;
             uint32_t zb;

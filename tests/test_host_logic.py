@@ -102,3 +102,44 @@ def test_miou_parity_recipe_on_the_oracle():
     bad = ref64.argmax(1).copy()
     bad[: bad.shape[0] // 4] = 3
     assert miou_parity(bad, ref64.argmax(1), labels, mask, C)["abs_diff"] > 1.0
+
+
+def test_fused_sampling_entry_point_rejects_cpu_tensors_and_bad_shapes():
+    """The opt-in fused caller path has no CPU fallback either, and validates its shapes before touching the library."""
+    from gaussianformer_b200.ops import deformable_aggregation_fused
+    from gaussianformer_b200.synthetic import make_daf_fused_inputs
+    from gaussianformer_b200.ops.deformable_aggregation import feature_maps_format
+    fms, loc, logits, pm, _ = make_daf_fused_inputs(num_anchor=6, num_pts=2, batch=1, num_cams=2, embed_dims=8,
+                                                    num_groups=2, levels=((4, 4),), seed=1)
+    feat, shape, start = feature_maps_format(fms)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        deformable_aggregation_fused(feat.contiguous(), shape, start, loc, logits, pm)
+    with pytest.raises(ValueError, match="weight_logits must be"):
+        deformable_aggregation_fused(feat.contiguous(), shape, start, loc, logits.flatten(1, 2), pm)
+
+
+def test_fused_reference_composition_matches_masked_softmax_definition():
+    """synthetic.reference_fused_composition (the PyTorch route the fused op replaces, used by bench.py and the GPU
+    tests) against a direct per-anchor evaluation: softmax over the unmasked (key point, camera, level) entries of each
+    group, zero weights for a group with every entry masked."""
+    from gaussianformer_b200.synthetic import reference_fused_composition
+    B, A, K, M, L, Gr, C = 1, 3, 2, 2, 2, 2, 4
+    gen = torch.Generator().manual_seed(0)
+    logits = torch.randn(B, A, K, M, L, Gr, generator=gen, dtype=torch.float64)
+    pm = torch.rand(B, A, K, M, generator=gen) > 0.4
+    pm[0, 1] = False
+    vals = torch.randn(B, A * K, M, L, C, generator=gen, dtype=torch.float64)     # stand-in for the sampled features
+
+    def fake_daf(feat, shape, start, loc, w):                                      # out[b,p,c] = sum_{m,l} w * val
+        return (w.repeat_interleave(C // Gr, dim=-1) * vals).sum(dim=(2, 3))
+    out = reference_fused_composition(fake_daf, None, None, None, None, logits, pm)
+    want = torch.zeros(B, A, C, dtype=torch.float64)
+    for a in range(A):
+        for g in range(Gr):
+            on = pm[0, a][:, :, None].expand(K, M, L)
+            if on.any():
+                w = torch.where(on, logits[0, a, ..., g], torch.tensor(-float("inf"), dtype=torch.float64)).flatten().softmax(0).reshape(K, M, L)
+                for c in range(g * (C // Gr), (g + 1) * (C // Gr)):
+                    want[0, a, c] = (w * vals[0].reshape(A, K, M, L, C)[a, ..., c]).sum()
+    assert torch.allclose(out, want, atol=1e-12)
+    assert torch.all(out[0, 1] == 0)

@@ -177,6 +177,9 @@ class DeformableAggregationFusedFunction(Function):
             mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weight_logits)
         if sampling_location.shape != (B, A * K, M, 2):
             raise ValueError(f"sampling_location must be [B, A*K, M, 2] = {(B, A * K, M, 2)}, got {tuple(sampling_location.shape)}")
+        if mc_ms_feat.dim() != 4 or mc_ms_feat.shape[0] != B or mc_ms_feat.shape[1] != M or spatial_shape.shape[0] != L:
+            raise ValueError(f"feature table [B, M, F, C] / level table do not match the weights: feat {tuple(mc_ms_feat.shape)}, "
+                             f"levels {spatial_shape.shape[0]}, weights B={B} M={M} L={L}")
         masks = []
         for name, mk, shape in (("point_mask", point_mask, (B, A, K, M)), ("weight_mask", weight_mask, (B, A, K, M, L, Gr))):
             if mk is not None:

@@ -485,6 +485,24 @@ def side_measurements(dev, kw, inp0, resident, desc):
     except Exception as e:
         out["daf_fused_error"] = repr(e)
     try:
+        # the reference's own fallback for the sampling op (PyTorch grid_sample route, deformable_module.py:307-353,
+        # restated in oracle.daf_torch_fallback) on the host cores, on a bounded sample of the same workload
+        import oracle
+        fms, loc, w = make_daf_inputs(seed=0)
+        nsub = 23040                                        # one tenth of the 230 400 sampling points
+        loc_s, w_s = loc[:, :nsub].contiguous(), w[:, :nsub].contiguous()
+        with torch.no_grad():
+            oracle.daf_torch_fallback(fms, loc_s, w_s, 4)
+            t0 = time.perf_counter()
+            oracle.daf_torch_fallback(fms, loc_s, w_s, 4)
+            sec = time.perf_counter() - t0
+        out["daf_cpu_fallback"] = {"ms_per_full_call_extrapolated": sec * 1e3 * loc.shape[1] / nsub, "sample_ms": sec * 1e3,
+                                   "sample": f"{nsub} of {loc.shape[1]} sampling points, 6 cameras x 4 levels, C = 128",
+                                   "cores": torch.get_num_threads(), "kind": "port",
+                                   "what": "reference's PyTorch fallback of the op (grid_sample + weighted fusion) on the host"}
+    except Exception as e:
+        out["daf_cpu_fallback"] = {"error": repr(e)}
+    try:
         from oracle import build_ref
         if build_ref.available("gf_ref_daf"):
             mod = build_ref.load_ref("gf_ref_daf")

@@ -302,3 +302,26 @@ def daf_fused_backward(feat, shape, start, loc, logits, g_out, point_mask=None, 
     inner = (w * g_w).sum(axis=(2, 3, 4), keepdims=True)
     # masked entries carry w = 0 (their logit was overwritten, :216-217) and all_miss groups have w = 0 throughout
     return g_feat, g_loc, w * (g_w - inner)
+
+
+# --------------------------------------------------------------------------- the reference's own PyTorch fallback of the op
+def daf_torch_fallback(feature_maps, loc, weights, num_groups):
+    """``DeformableFeatureAggregation.feature_sampling`` + ``multi_view_level_fusion``
+    (model/encoder/gaussian_encoder/deformable_module.py:307-353), the path the reference takes when its CUDA op is
+    not importable, restated on the op's own inputs: ``grid_sample(align_corners=False, padding_mode="zeros")`` per
+    level, the strict (0,1) camera gate of the op, weighted sum over cameras and levels.  ``feature_maps``: list of
+    ``[B, M, C, h, w]`` tensors, ``loc`` ``[B, P, M, 2]``, ``weights`` ``[B, P, M, L, Gr]``; returns ``[B, P, C]``.
+    Differentiable (used as an autograd reference by the tests and timed on the host by bench.py)."""
+    import torch
+    import torch.nn.functional as F
+    B, P, M, _ = loc.shape
+    C = feature_maps[0].shape[2]
+    gate = ((loc > 0) & (loc < 1)).all(-1)                        # B,P,M
+    grid = (loc * 2 - 1).permute(0, 2, 1, 3).reshape(B * M, P, 1, 2)
+    out = 0
+    for l, fm in enumerate(feature_maps):
+        s = F.grid_sample(fm.flatten(0, 1), grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+        s = s.reshape(B, M, C, P).permute(0, 3, 1, 2)               # B,P,M,C
+        wl = weights[:, :, :, l, :].repeat_interleave(C // num_groups, dim=-1)
+        out = out + (s * wl * gate[..., None]).sum(2)
+    return out

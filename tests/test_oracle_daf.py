@@ -11,18 +11,7 @@ from gaussianformer_b200.ops.deformable_aggregation import feature_maps_format
 
 def _dense_daf(feature_maps, loc, w, num_groups):
     """out[b,p,c] = sum_cam gate * sum_lvl w * grid_sample(feat)[c]   (float64, autograd-able)."""
-    B, P, M, _ = loc.shape
-    C = feature_maps[0].shape[2]
-    gate = ((loc > 0) & (loc < 1)).all(-1)                        # B,P,M
-    grid = (loc * 2 - 1).permute(0, 2, 1, 3).reshape(B * M, P, 1, 2)
-    out = 0
-    for l, fm in enumerate(feature_maps):
-        s = F.grid_sample(fm.flatten(0, 1), grid, mode="bilinear", padding_mode="zeros",
-                          align_corners=False)                      # B*M,C,P,1
-        s = s.reshape(B, M, C, P).permute(0, 3, 1, 2)               # B,P,M,C
-        wl = w[:, :, :, l, :].repeat_interleave(C // num_groups, dim=-1)   # B,P,M,C
-        out = out + (s * wl * gate[..., None]).sum(2)
-    return out
+    return oracle.daf_torch_fallback(feature_maps, loc, w, num_groups)
 
 
 def test_daf_forward_and_backward_match_grid_sample():

@@ -23,6 +23,8 @@
 //
 // Points that are not in canonical voxel order are detected per thread (W row forced to zero) and
 // evaluated afterwards by render_one_point(), so no second kernel is needed when N == H*W*D.
+#include <cstdlib>
+
 #include "splat_render.cuh"
 
 namespace gf {
@@ -456,6 +458,379 @@ __global__ void __launch_bounds__(kTcThreads + 32, 6) render_tc_kernel(const Ren
 }
 
 // ------------------------------------------------------------------------------------------------
+// Third-generation tcgen05 render kernel (GF_B200_RENDER=tc2; base variant; prepared for measurement, see
+// DESIGN.md 7): same UMMA / TMEM / mbarrier plumbing as render_tc_kernel above, different W producer.
+//
+// render_tc_kernel evaluates one voxel per thread: every thread re-reads every record and pays the whole quadratic
+// form per slot (~25 instructions), which is why it loses to the SIMT kernel.  Here a producer thread owns one
+// COLUMN of the 4 x 4 x 8 tile (8 z voxels that share x and y) and 4 consecutive Gaussians of a 32-Gaussian batch:
+// the x/y part of the exponent is evaluated once per (column, Gaussian), each slot then costs one FMA pair in dz,
+// one ex2, the box mask and the TF32 split, and the four Gaussians of a row go out as ONE 16-byte store per operand
+// (the K-major canonical layout keeps 4 consecutive k of a row contiguous).  Rows are ordered r = 16*z + column and
+// lane <-> (column mod 8) so that the eight lanes of a quarter warp hit eight different 16-byte bank groups.
+// CTAs whose 128 points are not voxel centres of their columns in canonical order take the exact per-point path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kT2K = 32;   // Gaussians per operand tile (4 MMA k-steps)
+
+template <int C>
+struct Tc2Smem {
+    static constexpr int REC = rec_floats(C);
+    alignas(128) float rec[2][kT2K * REC];
+    alignas(128) uint32_t a_hi[128 * kT2K];
+    alignas(128) uint32_t a_lo[128 * kT2K];
+    alignas(128) uint32_t b_hi[kTcN * kT2K];
+    alignas(128) uint32_t b_lo[kTcN * kT2K];
+    alignas(16) float4 pts[128];               // (x, y, z, live) of row r = 16*z + column
+    alignas(8) uint2 list[kTcSeg + kT2K];
+    alignas(8) uint64_t bar_rec[2];
+    alignas(8) uint64_t bar_full;
+    alignas(8) uint64_t bar_free;
+    uint32_t tmem_base;
+    int warp_count[2][kTcThreads / 32];
+    int nlist, last;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kTcThreads + 32, 4) render_tc2_kernel(const RenderParams p) {
+    constexpr int REC = rec_floats(C);
+    static_assert(REC == 32, "one record = 128 bytes = 8 cp.async chunks");
+    static_assert(C <= kTcN, "class count exceeds the MMA N tile");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Tc2Smem<C> &sm = *reinterpret_cast<Tc2Smem<C> *>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_compute = warp < kTcThreads / 32;
+    const int H = p.d.H, W = p.d.W, D = p.d.D;
+    const int binX0 = blockIdx.z * kTcBinX, binY0 = blockIdx.y * kTcBinY, binZ0 = blockIdx.x * kTcBinZ;
+
+    // ---- epilogue role: thread tid < 128 owns row r = tid = 16*z + column, column = 4*cy + cx ----------------
+    const int ez = (tid >> 4) & 7, ecol = tid & 15;
+    const int X = binX0 + (ecol & 3), Y = binY0 + (ecol >> 2), Z = binZ0 + ez;
+    const bool valid = is_compute && X < H && Y < W && Z < D;
+    const long long n = (static_cast<long long>(X) * W + Y) * D + Z;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    bool canon = false;
+    if (valid) {
+        px = __ldg(p.pts + 3 * n); py = __ldg(p.pts + 3 * n + 1); pz = __ldg(p.pts + 3 * n + 2);
+        int ix, iy, iz;
+        if (p.points_int) {
+            ix = p.points_int[3 * n]; iy = p.points_int[3 * n + 1]; iz = p.points_int[3 * n + 2];
+        } else {
+            ix = voxel_coord(px, p.d.pc_min[0], p.d.grid_size);
+            iy = voxel_coord(py, p.d.pc_min[1], p.d.grid_size);
+            iz = voxel_coord(pz, p.d.pc_min[2], p.d.grid_size);
+        }
+        canon = ix == X && iy == Y && iz == Z;
+        if (!canon) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
+    }
+    if (is_compute) sm.pts[tid] = make_float4(px, py, pz, (valid && canon) ? 1.f : 0.f);
+
+    // ---- one-time setup: barriers, tensor memory, zeroed S tiles --------------------------------------------
+    if (tid == 0) {
+        mbar_init(&sm.bar_rec[0], 32);
+        mbar_init(&sm.bar_rec[1], 32);
+        mbar_init(&sm.bar_full, kTcThreads);
+        mbar_init(&sm.bar_free, 1);
+        mbar_fence_init();
+    }
+    if (!is_compute) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
+                     "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = tid; i < kTcN * kT2K / 4; i += kTcThreads + 32) {
+        reinterpret_cast<uint4 *>(sm.b_hi)[i] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4 *>(sm.b_lo)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    // ---- producer role: column pcol of the tile, Gaussians 4*kgrp .. 4*kgrp+3 of every batch --------------------
+    const int pcol = (lane & 7) + 8 * ((lane >> 3) & 1), kgrp = (warp & 3) * 2 + (lane >> 4);
+    float cpx = 0.f, cpy = 0.f, cpz[kTcBinZ];
+    bool col_fast = true;
+#pragma unroll
+    for (int z = 0; z < kTcBinZ; ++z) {
+        const float4 q = sm.pts[16 * z + pcol];
+        if (z == 0) { cpx = q.x; cpy = q.y; }
+        cpz[z] = q.z;
+        col_fast = col_fast && q.w != 0.f && q.x == cpx && q.y == cpy;
+    }
+    const int cta_fast = __syncthreads_and((!is_compute || col_fast) ? 1 : 0);
+    const uint32_t col_bits = (1u << (pcol & 3)) | (1u << (4 + (pcol >> 2)));   // entry word: x mask [0,4) | y mask [4,8) | z mask [8,16)
+
+    uint32_t gc = 0;   // batches processed so far by this CTA
+    if (cta_fast) {
+    const int st_shift = 31 - __clz(p.st);
+    const int s = (binX0 >> st_shift) * p.nsy + (binY0 >> st_shift);
+    const int ncand = p.counts[s];
+    const int32_t *cand = p.lists + static_cast<size_t>(s) * p.d.G;
+    const uint32_t bX1 = min(binX0 + kTcBinX, H) - 1, bY1 = min(binY0 + kTcBinY, W) - 1, bZ1 = min(binZ0 + kTcBinZ, D) - 1;
+    // byte offset of my column's rows inside an A tile: row r = 16*z + pcol -> (r%8)*16 + (r/8)*SBO + (k/4)*LBO
+    const uint32_t a_col = (pcol & 7) * 16 + (pcol >> 3) * kSboA + kgrp * kLboA;
+
+    int cpos = 0;
+    bool last;
+    do {
+        // ======================= Phase A (compute warps): ordered survivors of the box test ===========
+        if (is_compute) {
+            int nlist = 0;
+            while (cpos < ncand && nlist + kTcThreads <= kTcSeg) {
+                constexpr int kPre = 4;
+                int gg[kPre];
+                uint4 bb[kPre];
+#pragma unroll
+                for (int u = 0; u < kPre; ++u) {
+                    const int i = cpos + u * kTcThreads + tid;
+                    gg[u] = i < ncand ? __ldg(cand + i) : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < kPre; ++u)
+                    bb[u] = gg[u] >= 0 ? __ldg(reinterpret_cast<const uint4 *>(p.boxes) + gg[u]) : make_uint4(1u, 1u, 1u, 1u);
+#pragma unroll
+                for (int u = 0; u < kPre; ++u) {
+                    if (cpos >= ncand || nlist + kTcThreads > kTcSeg) break;   // uniform
+                    const uint4 b = bb[u];
+                    const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16,
+                                   z0 = b.z & 0xffffu, z1 = b.z >> 16;
+                    const bool hit = gg[u] >= 0 && x0 <= bX1 && x1 >= static_cast<uint32_t>(binX0) && y0 <= bY1 &&
+                                     y1 >= static_cast<uint32_t>(binY0) && z0 <= bZ1 && z1 >= static_cast<uint32_t>(binZ0) &&
+                                     b.w == 0u;
+                    const int rx0 = max(static_cast<int>(x0) - binX0, 0), rx1 = min(static_cast<int>(x1) - binX0, kTcBinX - 1);
+                    const int ry0 = max(static_cast<int>(y0) - binY0, 0), ry1 = min(static_cast<int>(y1) - binY0, kTcBinY - 1);
+                    const int rz0 = max(static_cast<int>(z0) - binZ0, 0), rz1 = min(static_cast<int>(z1) - binZ0, kTcBinZ - 1);
+                    const uint32_t xm = ((2u << rx1) - 1u) & ~((1u << rx0) - 1u);
+                    const uint32_t ym = ((2u << ry1) - 1u) & ~((1u << ry0) - 1u);
+                    const uint32_t zm = ((2u << rz1) - 1u) & ~((1u << rz0) - 1u);
+                    const uint2 entry = make_uint2(xm | (ym << 4) | (zm << 8), static_cast<uint32_t>(gg[u]));
+                    const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+                    if (lane == 0) sm.warp_count[u & 1][warp] = __popc(ballot);
+                    compute_warps_sync();
+                    int off = nlist, total = 0;
+#pragma unroll
+                    for (int k = 0; k < kTcThreads / 32; ++k) {
+                        const int c = sm.warp_count[u & 1][k];
+                        if (k < warp) off += c;
+                        total += c;
+                    }
+                    if (hit) sm.list[off + __popc(ballot & lanemask_lt())] = entry;
+                    nlist += total;
+                    cpos += kTcThreads;
+                }
+                compute_warps_sync();
+            }
+            // pad the last batch with empty entries (mask 0 never matches)
+            if (tid < kT2K && nlist + tid < ((nlist + kT2K - 1) / kT2K) * kT2K) sm.list[nlist + tid] = make_uint2(0u, 0u);
+            if (tid == 0) {
+                sm.nlist = nlist;
+                sm.last = cpos >= ncand ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        const int nlist = sm.nlist;
+        last = sm.last != 0;
+        const int nchunks = (nlist + kT2K - 1) / kT2K;
+
+        if (!is_compute) {
+            // ======================= control warp: record ring + tensor-core issue ========================
+            auto load_records = [&](int k, uint32_t g_index) {   // batch k of this segment -> ring slot g_index & 1
+                const int slot = g_index & 1;
+#pragma unroll
+                for (int q = 0; q < kT2K * 8 / 32; ++q) {          // 32 records x 8 chunks of 16 bytes = 256 copies
+                    const int piece = lane + 32 * q, row = piece >> 3, col = (piece & 7) * 4;
+                    if (k * kT2K + row < nlist) {
+                        const uint32_t g = sm.list[k * kT2K + row].y;
+                        cp_async_16(&sm.rec[slot][row * REC + col], p.records + static_cast<size_t>(g) * REC + col);
+                    }
+                }
+                cp_async_arrive(&sm.bar_rec[slot]);
+            };
+            const uint32_t a_hi = smem_u32(sm.a_hi), a_lo = smem_u32(sm.a_lo);
+            const uint32_t b_hi = smem_u32(sm.b_hi), b_lo = smem_u32(sm.b_lo);
+            if (nchunks > 0) load_records(0, gc);
+            if (nchunks > 1) load_records(1, gc + 1);
+            for (int k = 0; k < nchunks; ++k, ++gc) {
+                uint32_t spins = 0;
+                while (!mbar_try_wait(&sm.bar_full, gc & 1)) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 22)) __trap();
+                }
+                if (lane == 0) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < kT2K / 8; ++ks) {
+                        const uint64_t dah = umma_smem_desc(a_hi + ks * 2 * kLboA, kLboA, kSboA);
+                        const uint64_t dal = umma_smem_desc(a_lo + ks * 2 * kLboA, kLboA, kSboA);
+                        const uint64_t dbh = umma_smem_desc(b_hi + ks * 2 * kLboB, kLboB, kSboB);
+                        const uint64_t dbl = umma_smem_desc(b_lo + ks * 2 * kLboB, kLboB, kSboB);
+                        umma_tf32(tmem, dah, dbh, (gc > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(tmem, dal, dbh, 1u);
+                        umma_tf32(tmem, dah, dbl, 1u);
+                    }
+                    umma_commit(&sm.bar_free);
+                }
+                __syncwarp();
+                if (k + 2 < nchunks) load_records(k + 2, gc + 2);   // ring slot gc & 1 is free again
+            }
+        } else {
+            // ======================= compute warps: W / S tiles ===========================================
+            for (int k = 0; k < nchunks; ++k, ++gc) {
+                const int slot = gc & 1;
+                const int cnt = min(kT2K, nlist - k * kT2K);
+                mbar_wait(&sm.bar_rec[slot], (gc >> 1) & 1);
+
+                // ---- my column x my four Gaussians: E for 8 z each; selects AFTER the arithmetic (padded slots hold
+                //      stale bytes that must never leak a NaN into W) ------------------------------------------------
+                float e[4][kTcBinZ];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = 4 * kgrp + i;
+                    const uint32_t ent = sm.list[k * kT2K + j].x;
+                    const float4 *r4 = reinterpret_cast<const float4 *>(&sm.rec[slot][j * REC]);
+                    const float4 g0 = r4[0], g1 = r4[1];
+                    const float2 g2 = *reinterpret_cast<const float2 *>(r4 + 2);
+                    const uint32_t zm = ((ent & col_bits) == col_bits) ? (ent >> 8) & 0xffu : 0u;
+                    const float dx = g0.x - cpx, dy = g0.y - cpy;
+                    float t1 = g1.x * dx;
+                    t1 = fmaf(g1.w, dy, t1);
+                    float A = t1 * dx;
+                    A = fmaf(g1.y * dy, dy, A);
+                    const float B = fmaf(g2.x, dy, g2.y * dx);
+#pragma unroll
+                    for (int z = 0; z < kTcBinZ; ++z) {
+                        const float dz = g0.z - cpz[z];
+                        const float q = fmaf(fmaf(g1.z, dz, B), dz, A);
+                        const float Eraw = ex2_approx(q);
+                        e[i][z] = ((zm >> z) & 1u) ? Eraw : 0.f;     // base variant: the opacity rides in S
+                    }
+                }
+                // ---- S tile values: lane -> (class mod 8, kk mod 4) keeps the scalar stores conflict-free ---------
+                const int nn_low = lane >> 2;
+                constexpr int kNg = (C + 7) / 8;
+                float sv[2][kNg];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int kk = (lane & 3) + 4 * (warp & 3) + 16 * h2;
+#pragma unroll
+                    for (int e8 = 0; e8 < kNg; ++e8) {
+                        const int nn = nn_low + 8 * e8;
+                        sv[h2][e8] = (kk < cnt && nn < C) ? sm.rec[slot][kk * REC + kGeomFloats + nn] : 0.f;
+                    }
+                }
+
+                // ---- the operand tiles are free once the previous batch's MMAs have completed -----------
+                if (gc > 0) mbar_wait(&sm.bar_free, (gc - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int z = 0; z < kTcBinZ; ++z) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float v = e[i][z];
+                        hi[i] = __float_as_uint(v) & 0xFFFFE000u;
+                        lo[i] = __float_as_uint(v - __uint_as_float(hi[i]));
+                    }
+                    const uint32_t off = a_col + 2 * z * kSboA;   // rows 16*z + pcol: (r/8) = 2*z + pcol/8
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.a_hi) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(sm.a_lo) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int kk = (lane & 3) + 4 * (warp & 3) + 16 * h2;
+#pragma unroll
+                    for (int e8 = 0; e8 < kNg; ++e8) {
+                        const int nn = nn_low + 8 * e8;
+                        const uint32_t off = (nn & 7) * 16 + (nn >> 3) * kSboB + (kk >> 2) * kLboB + (kk & 3) * 4;
+                        const uint32_t hi = __float_as_uint(sv[h2][e8]) & 0xFFFFE000u;
+                        const uint32_t lo = __float_as_uint(sv[h2][e8] - __uint_as_float(hi));
+                        *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sm.b_hi) + off) = hi;
+                        *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sm.b_lo) + off) = lo;
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(&sm.bar_full);
+            }
+        }
+        __syncthreads();
+    } while (!last);
+    }   // cta_fast
+
+    // ---- epilogue: accumulator row -> logits ------------------------------------------------------
+    if (is_compute) {
+        if (cta_fast) {
+            float acc[32];
+            if (gc > 0) {
+                mbar_wait(&sm.bar_free, (gc - 1) & 1);
+                tc_fence_after();
+                tmem_load_32(tmem + (static_cast<uint32_t>(warp * 32) << 16), acc);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+            }
+            if (valid) {
+                float *dst = p.out.logits + n * C;
+                if (p.out.argmax) {
+                    int best = 0;
+                    float bv = acc[0];
+#pragma unroll
+                    for (int c = 1; c < C; ++c)
+                        if (acc[c] > bv) { bv = acc[c]; best = c; }
+                    p.out.argmax[n] = static_cast<uint8_t>(best);
+                }
+                if ((C & 1) == 0) {
+#pragma unroll
+                    for (int c = 0; c < C; c += 2) __stcs(reinterpret_cast<float2 *>(dst + c), make_float2(acc[c], acc[c + 1]));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) dst[c] = acc[c];
+                }
+            }
+        } else if (valid) {
+            render_one_point<C, false>(p, n, px, py, pz);   // exact per-point path for this CTA's voxels
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (!is_compute) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+    }
+}
+
+template <int C>
+static int launch_render_tc2_t(const RenderParams &rp_in, cudaStream_t stream) {
+    RenderParams rp = rp_in;
+    rp.nby = (rp.d.W + kTcBinY - 1) / kTcBinY;
+    rp.nzc = (rp.d.D + kTcBinZ - 1) / kTcBinZ;
+    const int nbx = (rp.d.H + kTcBinX - 1) / kTcBinX;
+    GF_REQUIRE(rp.nby <= 65535 && nbx <= 65535, GF_ERR_UNSUPPORTED, "splat: grid too large for the render launch");
+    const dim3 grid(rp.nzc, rp.nby, nbx);
+    const size_t smem = sizeof(Tc2Smem<C>);
+    static bool configured = false;   // more than 48 KB of dynamic shared memory needs the opt-in
+    if (!configured) {
+        GF_CUDA_TRY(cudaFuncSetAttribute(render_tc2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = true;
+    }
+    if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_before, stream));
+    render_tc2_kernel<C><<<grid, kTcThreads + 32, smem, stream>>>(rp);
+    GF_CUDA_TRY(cudaGetLastError());
+    if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_after, stream));
+    return GF_OK;
+}
+
+static bool use_tc2() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("GF_B200_RENDER");
+        cached = (e && e[0] == 't' && e[1] == 'c' && e[2] == '2') ? 1 : 0;
+    }
+    return cached == 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int C, bool PROB>
@@ -476,6 +851,16 @@ static int launch_render_tc_t(const RenderParams &rp_in, cudaStream_t stream) {
 
 int launch_render_tc(const RenderParams &rp, cudaStream_t stream) {
     const bool prob = rp.d.variant == GF_SPLAT_PROB;
+    if (!prob && use_tc2()) {
+        switch (rp.d.C) {
+            case 16: return launch_render_tc2_t<16>(rp, stream);
+            case 17: return launch_render_tc2_t<17>(rp, stream);
+            case 18: return launch_render_tc2_t<18>(rp, stream);
+            case 19: return launch_render_tc2_t<19>(rp, stream);
+            case 20: return launch_render_tc2_t<20>(rp, stream);
+            default: break;
+        }
+    }
 #define GF_CASE(CC)                                                   \
     case CC:                                                          \
         return prob ? launch_render_tc_t<CC, true>(rp, stream)        \

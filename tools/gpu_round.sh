@@ -2,6 +2,9 @@
 # One GPU visit: parity tests, then A/B bench lines of the render-kernel variants (libraries built by
 # tools/build_variant.py), optionally ncu captures.  Usage (through gpurun):
 #   bash tools/gpu_round.sh <tag> "<variants>" [tests] [ncu] [full]
+# A variant is `default`, the name of a library built by tools/build_variant.py (e.g. `pipe2` after
+# `python tools/build_variant.py pipe2 -DGF_TILE_PIPE=2`), or `render:<x>` for GF_B200_RENDER=<x> (tc, tc2).
+# Every non-default variant first runs the splat parity tests, then two bench lines.
 set +e
 tag=${1:-x}; variants=${2:-default}; shift 2
 out=gpurun_out/$tag
@@ -15,9 +18,8 @@ for what in "$@"; do
   fi
 done
 for v in $variants; do
-  unset GF_B200_LIB GF_B200_SPLIT
-  if [ $v = nosplit ]; then export GF_B200_SPLIT=0;
-  elif [ ${v:0:5} = split ]; then export GF_B200_SPLIT=${v:5};
+  unset GF_B200_LIB GF_B200_RENDER
+  if [ ${v:0:7} = render: ]; then export GF_B200_RENDER=${v:7};      # e.g. render:tc2, render:tc
   elif [ $v != default ]; then export GF_B200_LIB=$PWD/gaussianformer_b200/csrc/variants/libgf_b200_$v.so; fi
   if [ $v != default ]; then
     timeout 600 python -m pytest tests/test_splat_gpu.py tests/test_cabi_gpu.py -m gpu -x -q 2>&1 | tail -1 | sed "s/^/$v parity: /"
@@ -34,7 +36,7 @@ except Exception as e:
 PY
   done
 done
-unset GF_B200_LIB GF_B200_SPLIT
+unset GF_B200_LIB GF_B200_RENDER
 for what in "$@"; do
   if [ $what = ncu ]; then
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \

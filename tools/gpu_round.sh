@@ -3,7 +3,7 @@
 # tools/build_variant.py), optionally ncu captures.  Usage (through gpurun):
 #   bash tools/gpu_round.sh <tag> "<variants>" [tests] [ncu] [full]
 # A variant is `default`, the name of a library built by tools/build_variant.py (e.g. `pipe2` after
-# `python tools/build_variant.py pipe2 -DGF_TILE_PIPE=2`), or `render:<x>` for GF_B200_RENDER=<x> (tc, tc2).
+# `python tools/build_variant.py pipe2 -DGF_TILE_PIPE=2`), `render:<x>` for GF_B200_RENDER=<x> (tc, tc2), or `st:<n>` for GF_B200_ST=<n>.
 # Every non-default variant first runs the splat parity tests, then two bench lines.
 set +e
 tag=${1:-x}; variants=${2:-default}; shift 2
@@ -19,7 +19,9 @@ for what in "$@"; do
 done
 for v in $variants; do
   unset GF_B200_LIB GF_B200_RENDER
+  unset GF_B200_ST
   if [ ${v:0:7} = render: ]; then export GF_B200_RENDER=${v:7};      # e.g. render:tc2, render:tc
+  elif [ ${v:0:3} = st: ]; then export GF_B200_ST=${v:3};            # supertile edge, e.g. st:8
   elif [ $v != default ]; then export GF_B200_LIB=$PWD/gaussianformer_b200/csrc/variants/libgf_b200_$v.so; fi
   if [ $v != default ]; then
     timeout 600 python -m pytest tests/test_splat_gpu.py tests/test_cabi_gpu.py -m gpu -x -q 2>&1 | tail -1 | sed "s/^/$v parity: /"
@@ -36,7 +38,7 @@ except Exception as e:
 PY
   done
 done
-unset GF_B200_LIB GF_B200_RENDER
+unset GF_B200_LIB GF_B200_RENDER GF_B200_ST
 for what in "$@"; do
   if [ $what = ncu ]; then
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \

@@ -224,6 +224,23 @@ class _LocalAggregatorBase(nn.Module):
         rotation quaternions instead of a precomputed inverse covariance and never leaves the device."""
         return self.forward(pts, means3D, opacities, semantics, scales, inverse_covariance_from_srt(scales, rotations))
 
+    def grid_points(self, device):
+        """``[1, H*W*D, 3]`` voxel-centre coordinates of this aggregator's grid on ``device``, built once with the
+        reference loader's arithmetic (``LoadOccupancySurroundOcc.get_meshgrid``, dataset/transform_3d.py:487-499:
+        ``arange * reso + 0.5 * reso + min`` in fp32, x-major) — the ``occ_xyz`` every shipped config feeds as ``pts``."""
+        cache = self.__dict__.setdefault("_grid_pts", {})
+        key = str(device)
+        if key not in cache:
+            from .synthetic import voxel_centers
+            cache[key] = voxel_centers((self.H, self.W, self.D), self._pc_min_host, float(self.grid_size)).reshape(1, -1, 3).to(device)
+        return cache[key]
+
+    def forward_on_grid(self, means3D, opacities, semantics, scales, cov3D):
+        """Entry point next to the reference signature: ``forward(pts = the grid's own voxel centres, ...)`` with the
+        points kept resident on the device (a caller that evaluates on the occupancy grid itself, as all shipped
+        configs do, then ships only the Gaussians).  Same kernels, same results as passing ``occ_xyz``."""
+        return self.forward(self.grid_points(means3D.device), means3D, opacities, semantics, scales, cov3D)
+
     def _run(self, pts, means3D, opacities, semantics, scales, cov3D):
         _require_cuda(pts, means3D, opacities, semantics, scales, cov3D)
         assert not pts.requires_grad

@@ -143,3 +143,19 @@ def test_fused_reference_composition_matches_masked_softmax_definition():
                     want[0, a, c] = (w * vals[0].reshape(A, K, M, L, C)[a, ..., c]).sum()
     assert torch.allclose(out, want, atol=1e-12)
     assert torch.all(out[0, 1] == 0)
+
+
+def test_grid_points_are_the_reference_loaders_voxel_centres():
+    """LocalAggregator.grid_points reproduces LoadOccupancySurroundOcc.get_meshgrid (dataset/transform_3d.py:487-499)
+    bit for bit: arange * reso + 0.5 * reso + min in fp32, stacked x-major."""
+    import local_aggregate
+    m = local_aggregate.LocalAggregator(3, 200, 200, 16, [-50.0, -50.0, -5.0], 0.5)
+    got = m.grid_points("cpu")
+    reso, grid, ranges = 0.5, [200, 200, 16], [-50, -50, -5.0]
+    xxx = torch.arange(grid[0], dtype=torch.float) * reso + 0.5 * reso + ranges[0]
+    yyy = torch.arange(grid[1], dtype=torch.float) * reso + 0.5 * reso + ranges[1]
+    zzz = torch.arange(grid[2], dtype=torch.float) * reso + 0.5 * reso + ranges[2]
+    want = torch.stack([xxx[:, None, None].expand(*grid), yyy[None, :, None].expand(*grid),
+                        zzz[None, None, :].expand(*grid)], dim=-1).reshape(1, -1, 3)
+    assert got.shape == (1, 640000, 3) and torch.equal(got, want)
+    assert m.grid_points("cpu") is got                       # cached

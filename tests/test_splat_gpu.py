@@ -341,3 +341,14 @@ def test_miou_is_unchanged():
     assert flips <= 3e-3 * ref.shape[0], f"{flips} arg-max differences on {ref.shape[0]} voxels"
     assert r["abs_diff"] <= 0.3, r
     assert r["ref"][0] > 50.0            # the labels are a meaningful target (10 % noise), not a degenerate score
+
+
+def test_forward_on_grid_is_forward_on_the_voxel_centres():
+    kw, inp, variant = h.splat_case("gs25600_solid", 7, False, dict(G=1500))
+    m = h.make_module(kw, variant)
+    t = h.to_dev(inp)
+    a = m(t["pts"], t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
+    b = m.forward_on_grid(t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
+    assert torch.equal(m.grid_points(a.device), t["pts"])      # the synthetic points ARE the loader's voxel centres
+    assert torch.equal(a, b)
+    assert "_grid_pts" not in m.state_dict() and list(m.state_dict().keys()) == ["pc_min"]

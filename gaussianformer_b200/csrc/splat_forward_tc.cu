@@ -831,6 +831,407 @@ static bool use_tc2() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fourth tcgen05 render kernel (GF_B200_RENDER=tc3; base variant; prepared for measurement, DESIGN.md 7 "tc3"):
+// the SIMT kernel's bin (8 x 4 columns x 16 z, one Phase A, one record ring) split into FOUR M = 128 tiles of
+// 4 x 4 columns x 8 z, one producer warp per tile.  A warp compacts, per batch of 32 listed Gaussians, the ones
+// that touch ITS tile into dense K positions (a tile therefore multiplies only its own Gaussians: 52 of the bin's
+// 98 on the nuScenes workload), evaluates W with the column-per-thread producer of render_tc2_kernel, writes its
+// own A / S operand tiles (K = 16) and issues its own tcgen05.mma into its own 32 TMEM columns; tcgen05.commit on a
+// per-warp mbarrier tells the warp when the tiles may be overwritten.  Rows of a tile: r = 16*z + column,
+// column = 4*cy + cx; lane = 16*khalf + column; a lane evaluates its column for the 4 consecutive K positions
+// 8*step + 4*khalf .. +3 and stores them as one 16-byte word per operand and z.
+// ------------------------------------------------------------------------------------------------
+constexpr int kT3K = 16;          // K positions per operand tile = two steps of 8 hits
+constexpr int kT3Batch = 32;      // list entries / records per ring slot
+constexpr int kT3Ring = 3;
+constexpr int kT3Seg = 512;
+constexpr uint32_t kT3TmemCols = 128;   // four accumulators of 32 columns
+
+template <int C>
+struct Tc3Smem {
+    static constexpr int REC = rec_floats(C);
+    alignas(128) float stage[kT3Ring][kT3Batch * REC];
+    alignas(128) uint32_t a_hi[4][128 * kT3K];
+    alignas(128) uint32_t a_lo[4][128 * kT3K];
+    alignas(128) uint32_t b_hi[4][kTcN * kT3K];
+    alignas(128) uint32_t b_lo[4][kTcN * kT3K];
+    alignas(16) float4 pts[512];                   // (x, y, z, live) of tile t, row r at [128*t + r]
+    alignas(8) uint2 list[kT3Seg + kT3Batch];      // x: x mask [0,8) | y mask [8,12) | z mask [16,32); y: Gaussian index
+    alignas(8) uint64_t bar_full[kT3Ring];
+    alignas(8) uint64_t bar_empty[kT3Ring];
+    alignas(8) uint64_t bar_mma[4];
+    uint32_t tmem_base;
+    int warp_count[2][4];
+    int hits[4][kT3Batch];
+    int nflush[4];
+};
+
+template <int C>
+__global__ void __launch_bounds__(128, 2) render_tc3_kernel(const RenderParams p) {
+    constexpr int REC = rec_floats(C);
+    constexpr int NT = 128;
+    static_assert(REC == 32, "one record = 128 bytes = 8 cp.async chunks");
+    static_assert(C <= 24, "the S tile writer covers 24 class rows");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Tc3Smem<C> &sm = *reinterpret_cast<Tc3Smem<C> *>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = p.d.H, W = p.d.W, D = p.d.D;
+    const int binX0 = blockIdx.z * kBinX, binY0 = blockIdx.y * kBinY, binZ0 = blockIdx.x * kBinZ;
+
+    // ---- my four voxels (one row of every tile): points, canonical check -> sm.pts -----------------------------------
+    const int rz = (tid >> 4) & 7, rcol = tid & 15;
+    auto voxel_of = [&](int t, int &X, int &Y, int &Z) {       // row tid of tile t
+        X = binX0 + 4 * (t & 1) + (rcol & 3);
+        Y = binY0 + (rcol >> 2);
+        Z = binZ0 + 8 * (t >> 1) + rz;
+    };
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        int X, Y, Z;
+        voxel_of(t, X, Y, Z);
+        const bool valid = X < H && Y < W && Z < D;
+        const long long n = (static_cast<long long>(X) * W + Y) * D + Z;
+        float x = 0.f, y = 0.f, z = 0.f;
+        bool canon = false;
+        if (valid) {
+            x = __ldg(p.pts + 3 * n); y = __ldg(p.pts + 3 * n + 1); z = __ldg(p.pts + 3 * n + 2);
+            int ix, iy, iz;
+            if (p.points_int) {
+                ix = p.points_int[3 * n]; iy = p.points_int[3 * n + 1]; iz = p.points_int[3 * n + 2];
+            } else {
+                ix = voxel_coord(x, p.d.pc_min[0], p.d.grid_size);
+                iy = voxel_coord(y, p.d.pc_min[1], p.d.grid_size);
+                iz = voxel_coord(z, p.d.pc_min[2], p.d.grid_size);
+            }
+            canon = ix == X && iy == Y && iz == Z;
+            if (!canon) atomicOr(p.flags, GF_FLAG_GENERIC_PATH);
+        }
+        sm.pts[128 * t + tid] = make_float4(x, y, z, (valid && canon) ? 1.f : 0.f);
+    }
+
+    // ---- one-time setup ----------------------------------------------------------------------------------------------
+    if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < kT3Ring; ++r) {
+            mbar_init(&sm.bar_full[r], NT);
+            mbar_init(&sm.bar_empty[r], 4);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) mbar_init(&sm.bar_mma[t], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
+                     "r"(kT3TmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid < 4) sm.nflush[tid] = 0;
+    // S tiles: class rows 24..31 are never written by the producers and must read as zero
+    for (int i = lane; i < kTcN * kT3K / 4; i += 32) {
+        reinterpret_cast<uint4 *>(sm.b_hi[warp])[i] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4 *>(sm.b_lo[warp])[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    // ---- producer role: warp = tile, lane = 16*khalf + column ---------------------------------------------------------
+    const int pcol = lane & 15, khalf = lane >> 4;
+    float cpx = 0.f, cpy = 0.f, cpz[8];
+    bool col_fast = true;
+#pragma unroll
+    for (int z = 0; z < 8; ++z) {
+        const float4 q = sm.pts[128 * warp + 16 * z + pcol];
+        if (z == 0) { cpx = q.x; cpy = q.y; }
+        cpz[z] = q.z;
+        col_fast = col_fast && q.w != 0.f && q.x == cpx && q.y == cpy;
+    }
+    const int cta_fast = __syncthreads_and(col_fast ? 1 : 0);
+    // my tile inside the bin: x bits 4*(warp&1) .. +3, all four y, z bits 8*(warp>>1) .. +7
+    const uint32_t tile_x = 0xFu << (4 * (warp & 1)), tile_z = 0xFFu << (16 + 8 * (warp >> 1));
+    const uint32_t col_x = 1u << (4 * (warp & 1) + (pcol & 3)), col_y = 1u << (8 + (pcol >> 2));
+    const int zshift = 16 + 8 * (warp >> 1);
+    const uint32_t a_col = (pcol & 7) * 16 + (pcol >> 3) * kSboA + khalf * kLboA;   // + (kfill/4)*LBO + 2*z*SBO
+    unsigned char *const my_a_hi = reinterpret_cast<unsigned char *>(sm.a_hi[warp]);
+    unsigned char *const my_a_lo = reinterpret_cast<unsigned char *>(sm.a_lo[warp]);
+    unsigned char *const my_b_hi = reinterpret_cast<unsigned char *>(sm.b_hi[warp]);
+    unsigned char *const my_b_lo = reinterpret_cast<unsigned char *>(sm.b_lo[warp]);
+    const uint32_t d_tmem = tmem + 32u * warp;      // my accumulator: columns 32*warp .. +31, all 128 lanes
+    int kfill = 0, nflush = 0;
+
+    // issue the MMAs of my tile for `ksteps` (1 or 2) k-steps of 8 and commit them on my barrier
+    auto flush = [&](int ksteps) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tc_fence_after();
+            const uint32_t ah = smem_u32(my_a_hi), al = smem_u32(my_a_lo), bh = smem_u32(my_b_hi), bl = smem_u32(my_b_lo);
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t dah = umma_smem_desc(ah + ks * 2 * kLboA, kLboA, kSboA);
+                const uint64_t dal = umma_smem_desc(al + ks * 2 * kLboA, kLboA, kSboA);
+                const uint64_t dbh = umma_smem_desc(bh + ks * 2 * kLboB, kLboB, kSboB);
+                const uint64_t dbl = umma_smem_desc(bl + ks * 2 * kLboB, kLboB, kSboB);
+                umma_tf32(d_tmem, dah, dbh, (nflush > 0 || ks > 0) ? 1u : 0u);
+                umma_tf32(d_tmem, dal, dbh, 1u);
+                umma_tf32(d_tmem, dah, dbl, 1u);
+            }
+            umma_commit(&sm.bar_mma[warp]);
+        }
+        __syncwarp();
+        ++nflush;
+        kfill = 0;
+    };
+
+    if (cta_fast) {
+    uint32_t gb = 0;   // batches consumed so far by this CTA (ring slots / parities)
+    const int st_shift = 31 - __clz(p.st);
+    const int s = (binX0 >> st_shift) * p.nsy + (binY0 >> st_shift);
+    const int ncand = p.counts[s];
+    const int32_t *cand = p.lists + static_cast<size_t>(s) * p.d.G;
+    const uint32_t bX1 = min(binX0 + kBinX, H) - 1, bY1 = min(binY0 + kBinY, W) - 1, bZ1 = min(binZ0 + kBinZ, D) - 1;
+
+    int cpos = 0;
+    while (cpos < ncand) {
+        __syncthreads();   // previous segment fully consumed
+        // ======================= Phase A: ordered survivors of the box test (as walk_tile, splat_tile.cuh) ==========
+        int nlist = 0;
+        while (cpos < ncand && nlist + NT <= kT3Seg) {
+            constexpr int kPre = 4;
+            int gg[kPre];
+            uint4 bb[kPre];
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) {
+                const int i = cpos + u * NT + tid;
+                gg[u] = i < ncand ? __ldg(cand + i) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < kPre; ++u)
+                bb[u] = gg[u] >= 0 ? __ldg(reinterpret_cast<const uint4 *>(p.boxes) + gg[u]) : make_uint4(1u, 1u, 1u, 1u);
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) {
+                if (cpos >= ncand || nlist + NT > kT3Seg) break;   // uniform
+                const uint4 b = bb[u];
+                const uint32_t x0 = b.x & 0xffffu, x1 = b.x >> 16, y0 = b.y & 0xffffu, y1 = b.y >> 16,
+                               z0 = b.z & 0xffffu, z1 = b.z >> 16;
+                const bool hit = gg[u] >= 0 && x0 <= bX1 && x1 >= static_cast<uint32_t>(binX0) && y0 <= bY1 &&
+                                 y1 >= static_cast<uint32_t>(binY0) && z0 <= bZ1 && z1 >= static_cast<uint32_t>(binZ0) &&
+                                 b.w == 0u;
+                const int rx0 = max(static_cast<int>(x0) - binX0, 0), rx1 = min(static_cast<int>(x1) - binX0, kBinX - 1);
+                const int ry0 = max(static_cast<int>(y0) - binY0, 0), ry1 = min(static_cast<int>(y1) - binY0, kBinY - 1);
+                const int rz0 = max(static_cast<int>(z0) - binZ0, 0), rz1 = min(static_cast<int>(z1) - binZ0, kBinZ - 1);
+                const uint32_t xm = ((2u << rx1) - 1u) & ~((1u << rx0) - 1u);
+                const uint32_t ym = ((2u << ry1) - 1u) & ~((1u << ry0) - 1u);
+                const uint32_t zm = ((2u << rz1) - 1u) & ~((1u << rz0) - 1u);
+                const uint2 entry = make_uint2(xm | (ym << 8) | (zm << 16), static_cast<uint32_t>(gg[u]));
+                const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) sm.warp_count[u & 1][warp] = __popc(ballot);
+                __syncthreads();
+                int off = nlist, total = 0;
+#pragma unroll
+                for (int k = 0; k < NT / 32; ++k) {
+                    const int c = sm.warp_count[u & 1][k];
+                    if (k < warp) off += c;
+                    total += c;
+                }
+                if (hit) sm.list[off + __popc(ballot & lanemask_lt())] = entry;
+                nlist += total;
+                cpos += NT;
+            }
+            __syncthreads();
+        }
+        if (tid < kT3Batch && nlist + tid < ((nlist + kT3Batch - 1) / kT3Batch) * kT3Batch) sm.list[nlist + tid] = make_uint2(0u, 0u);
+        __syncthreads();
+
+        // ======================= Phase B: record ring (full / empty mbarriers), one tile per warp ====================
+        const int nchunks = (nlist + kT3Batch - 1) / kT3Batch;
+        auto issue = [&](int k, uint32_t b_index) {
+            const int slot = b_index % kT3Ring;
+            const uint32_t use = b_index / kT3Ring;
+            if (use > 0) mbar_wait(&sm.bar_empty[slot], (use - 1) & 1);
+#pragma unroll
+            for (int q = 0; q < kT3Batch * 8 / NT; ++q) {
+                const int piece = tid + NT * q, row = piece >> 3, col = (piece & 7) * 4;
+                if (k * kT3Batch + row < nlist) {
+                    const uint32_t g = sm.list[k * kT3Batch + row].y;
+                    cp_async_16(&sm.stage[slot][row * REC + col], p.records + static_cast<size_t>(g) * REC + col);
+                }
+            }
+            cp_async_arrive(&sm.bar_full[slot]);
+        };
+#pragma unroll 1
+        for (int k = 0; k < kT3Ring - 1 && k < nchunks; ++k) issue(k, gb + k);
+#pragma unroll 1
+        for (int k = 0; k < nchunks; ++k, ++gb) {
+            const int slot = gb % kT3Ring;
+            // the entries of this batch that touch my tile, compacted in ascending order
+            const uint32_t ex = sm.list[k * kT3Batch + lane].x;
+            const bool touch = (ex & tile_x) != 0u && (ex & tile_z) != 0u;
+            const uint32_t tm = __ballot_sync(0xffffffffu, touch);
+            if (touch) sm.hits[warp][__popc(tm & lanemask_lt())] = lane;
+            const int nh = __popc(tm);
+            mbar_wait(&sm.bar_full[slot], (gb / kT3Ring) & 1);
+            __syncwarp();
+            const float *stg = sm.stage[slot];
+            for (int base = 0; base < nh; base += 8) {
+                if (kfill == 0 && nflush > 0) {            // my operand tiles are free once my previous MMAs have completed
+                    mbar_wait(&sm.bar_mma[warp], (nflush - 1) & 1);
+                    tc_fence_after();
+                }
+                // ---- W: my column x my 4 K positions (hits base + 4*khalf + i), 8 z each --------------------------------
+                float e[4][8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int hq = base + 4 * khalf + i;
+                    const bool live = hq < nh;
+                    const int j = live ? sm.hits[warp][hq] : 0;
+                    const uint32_t ent = sm.list[k * kT3Batch + j].x;
+                    const float4 *r4 = reinterpret_cast<const float4 *>(stg + j * REC);
+                    const float4 g0 = r4[0], g1 = r4[1];
+                    const float2 g2 = *reinterpret_cast<const float2 *>(r4 + 2);
+                    const uint32_t zm = (live && (ent & col_x) && (ent & col_y)) ? (ent >> zshift) & 0xffu : 0u;
+                    const float dx = g0.x - cpx, dy = g0.y - cpy;
+                    float t1 = g1.x * dx;
+                    t1 = fmaf(g1.w, dy, t1);
+                    float A = t1 * dx;
+                    A = fmaf(g1.y * dy, dy, A);
+                    const float B = fmaf(g2.x, dy, g2.y * dx);
+#pragma unroll
+                    for (int z = 0; z < 8; ++z) {
+                        const float dz = g0.z - cpz[z];
+                        const float q = fmaf(fmaf(g1.z, dz, B), dz, A);
+                        const float Eraw = ex2_approx(q);
+                        e[i][z] = ((zm >> z) & 1u) ? Eraw : 0.f;     // select after the arithmetic; the opacity rides in S
+                    }
+                }
+#pragma unroll
+                for (int z = 0; z < 8; ++z) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float v = e[i][z];
+                        hi[i] = __float_as_uint(v) & 0xFFFFE000u;
+                        lo[i] = __float_as_uint(v - __uint_as_float(hi[i]));
+                    }
+                    const uint32_t off = a_col + (kfill >> 2) * kLboA + 2 * z * kSboA;
+                    *reinterpret_cast<uint4 *>(my_a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(my_a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                // ---- S: K positions kfill + kq (+4), class rows nn_low + 8*e8; lane -> (nn_low, kq) is conflict-free --
+                {
+                    const int kq = lane & 3, nn_low = lane >> 2;
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int hq = base + kq + 4 * h2;
+                        const bool live = hq < nh;
+                        const int j = live ? sm.hits[warp][hq] : 0;
+                        const int kp = kfill + kq + 4 * h2;
+#pragma unroll
+                        for (int e8 = 0; e8 < 3; ++e8) {
+                            const int nn = nn_low + 8 * e8;
+                            const float v = (live && nn < C) ? stg[j * REC + kGeomFloats + nn] : 0.f;
+                            const uint32_t off = (nn & 7) * 16 + (nn >> 3) * kSboB + (kp >> 2) * kLboB + (kp & 3) * 4;
+                            const uint32_t hi = __float_as_uint(v) & 0xFFFFE000u;
+                            const uint32_t lo = __float_as_uint(v - __uint_as_float(hi));
+                            *reinterpret_cast<uint32_t *>(my_b_hi + off) = hi;
+                            *reinterpret_cast<uint32_t *>(my_b_lo + off) = lo;
+                        }
+                    }
+                }
+                kfill += 8;
+                if (kfill == kT3K) flush(2);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.bar_empty[slot]);
+            if (k + kT3Ring - 1 < nchunks) issue(k + kT3Ring - 1, gb + kT3Ring - 1);
+        }
+    }
+    if (kfill == 8) flush(1);          // half-filled tile: positions 0..7 only
+    if (lane == 0) sm.nflush[warp] = nflush;
+    }   // cta_fast
+    __syncthreads();
+
+    // ---- epilogue: thread tid reads row tid (TMEM lane tid) of all four accumulators -------------------------------
+#pragma unroll 1
+    for (int t = 0; t < 4; ++t) {
+        int X, Y, Z;
+        voxel_of(t, X, Y, Z);
+        const bool valid = X < H && Y < W && Z < D;
+        const long long n = (static_cast<long long>(X) * W + Y) * D + Z;
+        if (!cta_fast) {
+            const float4 q = sm.pts[128 * t + tid];
+            if (valid) render_one_point<C, false>(p, n, q.x, q.y, q.z);   // exact per-point path
+            continue;
+        }
+        float acc[32];
+        const int nf = sm.nflush[t];
+        if (nf > 0) {
+            mbar_wait(&sm.bar_mma[t], (nf - 1) & 1);
+            tc_fence_after();
+            tmem_load_32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + 32u * t, acc);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        }
+        if (valid) {
+            float *dst = p.out.logits + n * C;
+            if (p.out.argmax) {
+                int best = 0;
+                float bv = acc[0];
+#pragma unroll
+                for (int c = 1; c < C; ++c)
+                    if (acc[c] > bv) { bv = acc[c]; best = c; }
+                p.out.argmax[n] = static_cast<uint8_t>(best);
+            }
+            if ((C & 1) == 0) {
+#pragma unroll
+                for (int c = 0; c < C; c += 2) __stcs(reinterpret_cast<float2 *>(dst + c), make_float2(acc[c], acc[c + 1]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) dst[c] = acc[c];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kT3TmemCols));
+    }
+}
+
+template <int C>
+static int launch_render_tc3_t(const RenderParams &rp_in, cudaStream_t stream) {
+    RenderParams rp = rp_in;
+    rp.nby = (rp.d.W + kBinY - 1) / kBinY;
+    rp.nzc = (rp.d.D + kBinZ - 1) / kBinZ;
+    const int nbx = (rp.d.H + kBinX - 1) / kBinX;
+    GF_REQUIRE(rp.nby <= 65535 && nbx <= 65535, GF_ERR_UNSUPPORTED, "splat: grid too large for the render launch");
+    const dim3 grid(rp.nzc, rp.nby, nbx);
+    const size_t smem = sizeof(Tc3Smem<C>);
+    static bool configured = false;
+    if (!configured) {
+        GF_CUDA_TRY(cudaFuncSetAttribute(render_tc3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = true;
+    }
+    if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_before, stream));
+    render_tc3_kernel<C><<<grid, 128, smem, stream>>>(rp);
+    GF_CUDA_TRY(cudaGetLastError());
+    if (g_ev_before && g_ev_after) GF_CUDA_TRY(cudaEventRecord(g_ev_after, stream));
+    return GF_OK;
+}
+
+static bool use_tc3() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("GF_B200_RENDER");
+        cached = (e && e[0] == 't' && e[1] == 'c' && e[2] == '3') ? 1 : 0;
+    }
+    return cached == 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int C, bool PROB>
@@ -851,6 +1252,16 @@ static int launch_render_tc_t(const RenderParams &rp_in, cudaStream_t stream) {
 
 int launch_render_tc(const RenderParams &rp, cudaStream_t stream) {
     const bool prob = rp.d.variant == GF_SPLAT_PROB;
+    if (!prob && use_tc3()) {
+        switch (rp.d.C) {
+            case 16: return launch_render_tc3_t<16>(rp, stream);
+            case 17: return launch_render_tc3_t<17>(rp, stream);
+            case 18: return launch_render_tc3_t<18>(rp, stream);
+            case 19: return launch_render_tc3_t<19>(rp, stream);
+            case 20: return launch_render_tc3_t<20>(rp, stream);
+            default: break;
+        }
+    }
     if (!prob && use_tc2()) {
         switch (rp.d.C) {
             case 16: return launch_render_tc2_t<16>(rp, stream);

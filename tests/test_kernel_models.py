@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("script,expect", [
-    ("check_tc2_layout.py", "tc2 operand layout ok"),
+    ("check_tc2_layout.py", "tc3 operand layout ok"),
     ("emulate_tc2.py", "tc2 model matches the oracle"),
     ("emulate_tc3.py", "tc3 model matches the oracle"),
 ])

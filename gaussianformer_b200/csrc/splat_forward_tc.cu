@@ -841,6 +841,12 @@ static bool use_tc2() {
 // column = 4*cy + cx; lane = 16*khalf + column; a lane evaluates its column for the 4 consecutive K positions
 // 8*step + 4*khalf .. +3 and stores them as one 16-byte word per operand and z.
 // ------------------------------------------------------------------------------------------------
+// GF_TC3_HALF = 1 (unmeasured): the two 8-position halves of a warp's K = 16 operand tile are flushed separately, each
+// with its own completion barrier, so the warp fills one half while the tensor core reads the other instead of waiting
+// for its MMAs after every second step.
+#ifndef GF_TC3_HALF
+#define GF_TC3_HALF 0
+#endif
 constexpr int kT3K = 16;          // K positions per operand tile = two steps of 8 hits
 constexpr int kT3Batch = 32;      // list entries / records per ring slot
 constexpr int kT3Ring = 3;
@@ -859,11 +865,11 @@ struct Tc3Smem {
     alignas(8) uint2 list[kT3Seg + kT3Batch];      // x: x mask [0,8) | y mask [8,12) | z mask [16,32); y: Gaussian index
     alignas(8) uint64_t bar_full[kT3Ring];
     alignas(8) uint64_t bar_empty[kT3Ring];
-    alignas(8) uint64_t bar_mma[4];
+    alignas(8) uint64_t bar_mma[4][2];             // [tile][half]; GF_TC3_HALF = 0 uses [tile][0] only
     uint32_t tmem_base;
     int warp_count[2][4];
     int hits[4][kT3Batch];
-    int nflush[4];
+    int nflush[4][2];
 };
 
 template <int C>
@@ -918,7 +924,10 @@ __global__ void __launch_bounds__(128, 2) render_tc3_kernel(const RenderParams p
             mbar_init(&sm.bar_empty[r], 4);
         }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) mbar_init(&sm.bar_mma[t], 1);
+        for (int t = 0; t < 4; ++t) {
+            mbar_init(&sm.bar_mma[t][0], 1);
+            mbar_init(&sm.bar_mma[t][1], 1);
+        }
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -926,7 +935,7 @@ __global__ void __launch_bounds__(128, 2) render_tc3_kernel(const RenderParams p
                      "r"(kT3TmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (tid < 4) sm.nflush[tid] = 0;
+    if (tid < 8) sm.nflush[tid >> 1][tid & 1] = 0;
     // S tiles: class rows 24..31 are never written by the producers and must read as zero
     for (int i = lane; i < kTcN * kT3K / 4; i += 32) {
         reinterpret_cast<uint4 *>(sm.b_hi[warp])[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -960,6 +969,32 @@ __global__ void __launch_bounds__(128, 2) render_tc3_kernel(const RenderParams p
     unsigned char *const my_b_lo = reinterpret_cast<unsigned char *>(sm.b_lo[warp]);
     const uint32_t d_tmem = tmem + 32u * warp;      // my accumulator: columns 32*warp .. +31, all 128 lanes
     int kfill = 0, nflush = 0;
+#if GF_TC3_HALF
+    int nfl[2] = {0, 0};   // flushes of each half so far
+
+    // issue the 3 MMAs of the half tile that was just filled (K positions kfill .. kfill+7) and commit them on its barrier
+    auto flush_half = [&]() {
+        const int half = kfill >> 3;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tc_fence_after();
+            const uint32_t ko = half * 2 * kLboA, kob = half * 2 * kLboB;
+            const uint64_t dah = umma_smem_desc(smem_u32(my_a_hi) + ko, kLboA, kSboA);
+            const uint64_t dal = umma_smem_desc(smem_u32(my_a_lo) + ko, kLboA, kSboA);
+            const uint64_t dbh = umma_smem_desc(smem_u32(my_b_hi) + kob, kLboB, kSboB);
+            const uint64_t dbl = umma_smem_desc(smem_u32(my_b_lo) + kob, kLboB, kSboB);
+            umma_tf32(d_tmem, dah, dbh, nflush > 0 ? 1u : 0u);
+            umma_tf32(d_tmem, dal, dbh, 1u);
+            umma_tf32(d_tmem, dah, dbl, 1u);
+            umma_commit(&sm.bar_mma[warp][half]);
+        }
+        __syncwarp();
+        ++nflush;
+        if (half) ++nfl[1]; else ++nfl[0];
+        kfill = (kfill + 8) & (kT3K - 1);
+    };
+#else
 
     // issue the MMAs of my tile for `ksteps` (1 or 2) k-steps of 8 and commit them on my barrier
     auto flush = [&](int ksteps) {
@@ -977,12 +1012,13 @@ __global__ void __launch_bounds__(128, 2) render_tc3_kernel(const RenderParams p
                 umma_tf32(d_tmem, dal, dbh, 1u);
                 umma_tf32(d_tmem, dah, dbl, 1u);
             }
-            umma_commit(&sm.bar_mma[warp]);
+            umma_commit(&sm.bar_mma[warp][0]);
         }
         __syncwarp();
         ++nflush;
         kfill = 0;
     };
+#endif
 
     if (cta_fast) {
     uint32_t gb = 0;   // batches consumed so far by this CTA (ring slots / parities)
@@ -1075,10 +1111,20 @@ __global__ void __launch_bounds__(128, 2) render_tc3_kernel(const RenderParams p
             __syncwarp();
             const float *stg = sm.stage[slot];
             for (int base = 0; base < nh; base += 8) {
+#if GF_TC3_HALF
+                {                                          // this half is free once ITS previous MMAs have completed
+                    const int half = kfill >> 3, done = half ? nfl[1] : nfl[0];
+                    if (done > 0) {
+                        mbar_wait(&sm.bar_mma[warp][half], (done - 1) & 1);
+                        tc_fence_after();
+                    }
+                }
+#else
                 if (kfill == 0 && nflush > 0) {            // my operand tiles are free once my previous MMAs have completed
-                    mbar_wait(&sm.bar_mma[warp], (nflush - 1) & 1);
+                    mbar_wait(&sm.bar_mma[warp][0], (nflush - 1) & 1);
                     tc_fence_after();
                 }
+#endif
                 // ---- W: my column x my 4 K positions (hits base + 4*khalf + i), 8 z each --------------------------------
                 float e[4][8];
 #pragma unroll
@@ -1139,16 +1185,24 @@ __global__ void __launch_bounds__(128, 2) render_tc3_kernel(const RenderParams p
                         }
                     }
                 }
+#if GF_TC3_HALF
+                flush_half();
+#else
                 kfill += 8;
                 if (kfill == kT3K) flush(2);
+#endif
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.bar_empty[slot]);
             if (k + kT3Ring - 1 < nchunks) issue(k + kT3Ring - 1, gb + kT3Ring - 1);
         }
     }
+#if GF_TC3_HALF
+    if (lane == 0) { sm.nflush[warp][0] = nfl[0]; sm.nflush[warp][1] = nfl[1]; }
+#else
     if (kfill == 8) flush(1);          // half-filled tile: positions 0..7 only
-    if (lane == 0) sm.nflush[warp] = nflush;
+    if (lane == 0) { sm.nflush[warp][0] = nflush; sm.nflush[warp][1] = 0; }
+#endif
     }   // cta_fast
     __syncthreads();
 
@@ -1165,9 +1219,10 @@ __global__ void __launch_bounds__(128, 2) render_tc3_kernel(const RenderParams p
             continue;
         }
         float acc[32];
-        const int nf = sm.nflush[t];
+        const int nf0 = sm.nflush[t][0], nf1 = sm.nflush[t][1], nf = nf0 + nf1;
         if (nf > 0) {
-            mbar_wait(&sm.bar_mma[t], (nf - 1) & 1);
+            if (nf0 > 0) mbar_wait(&sm.bar_mma[t][0], (nf0 - 1) & 1);
+            if (nf1 > 0) mbar_wait(&sm.bar_mma[t][1], (nf1 - 1) & 1);
             tc_fence_after();
             tmem_load_32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + 32u * t, acc);
         } else {

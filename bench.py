@@ -251,9 +251,9 @@ def main():
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 50))]
     for i, (a, b) in enumerate(evs):
         a.record(stream); b.record(stream)          # materialise the underlying cudaEvent_t
-        L.gf_splat_set_render_events(ctypes.c_void_p(a.cuda_event), ctypes.c_void_p(b.cuda_event))
+        L.gf_debug_set_render_events(ctypes.c_void_p(a.cuda_event), ctypes.c_void_p(b.cuda_event))
         step(i)
-    L.gf_splat_set_render_events(None, None)
+    L.gf_debug_set_render_events(None, None)
     torch.cuda.synchronize(dev)
     render_ms = sorted(a.elapsed_time(b) for a, b in evs)
     render_ms = sum(render_ms) / len(render_ms)

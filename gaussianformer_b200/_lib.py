@@ -20,11 +20,12 @@ GF_FLAG_MEAN_OUT_OF_GRID = 2
 GF_FLAG_RADIUS_LT_1 = 4
 GF_FLAG_GENERIC_PATH = 256
 
+DEBUG_EXPORTS = ("gf_debug_set_render_events",)   # include/gf_b200_debug.h: measurement hooks, not the drop-in boundary
 EXPORTS = (
     "gf_abi_version", "gf_last_error", "gf_splat_supported_classes",
     "gf_splat_forward_workspace_bytes", "gf_splat_backward_workspace_bytes",
     "gf_splat_forward", "gf_splat_backward", "gf_splat_read_flags",
-    "gf_daf_forward", "gf_daf_backward", "gf_daf_format", "gf_splat_set_render_events",
+    "gf_daf_forward", "gf_daf_backward", "gf_daf_format", "gf_splat_ce_partials",
     "gf_daf_fused_supported", "gf_daf_fused_forward", "gf_daf_fused_backward",
 )
 
@@ -33,25 +34,26 @@ class SplatDesc(Structure):
     _fields_ = [("G", c_int32), ("N", c_int32), ("C", c_int32), ("H", c_int32), ("W", c_int32), ("D", c_int32),
                 ("variant", c_int32), ("radii_axes", c_int32), ("cov_stride", c_int32),
                 ("pc_min", c_float * 3), ("grid_size", c_float), ("scale_multiplier", c_float),
-                ("radii_min", c_int32)]
+                ("radii_min", c_int32), ("batch", c_int32), ("pts_shared", c_int32)]
 
 
 class SplatInputs(Structure):
     _fields_ = [("pts", c_void_p), ("points_int", c_void_p), ("means", c_void_p), ("means_int", c_void_p),
                 ("opacities", c_void_p), ("semantics", c_void_p), ("cov", c_void_p), ("radii", c_void_p),
-                ("scales", c_void_p)]
+                ("scales", c_void_p), ("rotations", c_void_p)]
 
 
 class SplatOutputs(Structure):
     _fields_ = [("logits", c_void_p), ("bin_logits", c_void_p), ("density", c_void_p), ("probability", c_void_p),
-                ("argmax", c_void_p)]
+                ("argmax", c_void_p), ("logits_cn", c_void_p), ("labels", c_void_p), ("class_weights", c_void_p),
+                ("ce_partials", c_void_p)]
 
 
 class SplatGrads(Structure):
     _fields_ = [("logits_grad", c_void_p), ("bin_logits_grad", c_void_p), ("density_grad", c_void_p),
                 ("logits", c_void_p), ("bin_logits", c_void_p), ("probability", c_void_p),
                 ("means_grad", c_void_p), ("opacity_grad", c_void_p), ("semantics_grad", c_void_p),
-                ("cov_grad", c_void_p)]
+                ("cov_grad", c_void_p), ("scales_grad", c_void_p), ("rotations_grad", c_void_p)]
 
 
 class DafDesc(Structure):
@@ -99,14 +101,16 @@ def lib():
         L.gf_splat_backward.argtypes = [POINTER(SplatDesc), POINTER(SplatInputs), POINTER(SplatGrads), c_void_p,
                                         c_size_t, c_void_p]
         L.gf_splat_read_flags.argtypes = [c_void_p, c_void_p, POINTER(c_uint32)]
-        L.gf_splat_set_render_events.argtypes = [c_void_p, c_void_p]
+        L.gf_debug_set_render_events.argtypes = [c_void_p, c_void_p]
+        L.gf_splat_ce_partials.argtypes = [POINTER(SplatDesc)]
+        L.gf_splat_ce_partials.restype = c_int
         L.gf_daf_forward.argtypes = [POINTER(DafDesc)] + [c_void_p] * 7
         L.gf_daf_backward.argtypes = [POINTER(DafDesc)] + [c_void_p] * 10
         L.gf_daf_fused_supported.argtypes = [POINTER(DafFusedDesc)]
         L.gf_daf_fused_forward.argtypes = [POINTER(DafFusedDesc)] + [c_void_p] * 10
         L.gf_daf_fused_backward.argtypes = [POINTER(DafFusedDesc)] + [c_void_p] * 14
         L.gf_daf_format.argtypes = [POINTER(DafFormatDesc), POINTER(c_void_p), c_void_p, c_int, c_void_p]
-        if L.gf_abi_version() != 1:
+        if L.gf_abi_version() != 2:
             raise ImportError("libgf_b200.so: ABI version mismatch")
         _lib = L
     return _lib

@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "gf_b200_debug.h"
 
 namespace gf {
 
@@ -33,6 +34,7 @@ int launch_render(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_sp
 size_t backward_workspace_bytes(const gf_splat_desc &d);
 int launch_backward(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_splat_grads &gr, void *workspace,
                     int num_sms, cudaStream_t stream);
+int render_ctas_per_sample(const gf_splat_desc &d);
 extern thread_local cudaEvent_t g_ev_before, g_ev_after;
 extern const int kSupportedClasses[];
 extern const int kNumSupportedClasses;
@@ -90,6 +92,9 @@ static int check_desc(const gf_splat_desc *d) {
                "splat: unknown variant %d", d->variant);
     GF_REQUIRE(d->radii_axes == 1 || d->radii_axes == 3, GF_ERR_INVALID_ARG, "splat: radii_axes must be 1 or 3");
     GF_REQUIRE(d->cov_stride == 6 || d->cov_stride == 9, GF_ERR_INVALID_ARG, "splat: cov_stride must be 6 or 9");
+    GF_REQUIRE(d->batch >= 0 && d->batch <= 65535, GF_ERR_INVALID_ARG, "splat: batch=%d outside [0, 65535]", d->batch);
+    GF_REQUIRE(static_cast<long long>(batch_of(*d)) * d->N * d->C < (1ll << 40), GF_ERR_UNSUPPORTED,
+               "splat: batch x N x C too large");
     bool ok = false;
     for (int i = 0; i < kNumSupportedClasses; ++i) ok = ok || kSupportedClasses[i] == d->C;
     GF_REQUIRE(ok, GF_ERR_UNSUPPORTED, "splat: class count C=%d is not compiled in", d->C);
@@ -100,8 +105,10 @@ static int check_inputs(const gf_splat_desc *d, const gf_splat_inputs *in) {
     GF_REQUIRE(in != nullptr, GF_ERR_INVALID_ARG, "splat: inputs struct is NULL");
     if (d->N > 0) GF_REQUIRE(in->pts != nullptr, GF_ERR_INVALID_ARG, "splat: pts is NULL");
     if (d->G > 0) {
-        GF_REQUIRE(in->means && in->opacities && in->semantics && in->cov, GF_ERR_INVALID_ARG,
-                   "splat: means / opacities / semantics / cov must not be NULL");
+        GF_REQUIRE(in->means && in->opacities && in->semantics, GF_ERR_INVALID_ARG,
+                   "splat: means / opacities / semantics must not be NULL");
+        GF_REQUIRE(in->cov || (in->scales && in->rotations), GF_ERR_INVALID_ARG,
+                   "splat: need cov, or scales + rotations to build the inverse covariance from");
         GF_REQUIRE(in->radii || in->scales, GF_ERR_INVALID_ARG, "splat: need radii or scales");
         if (!in->means_int || !in->radii || !in->points_int)
             GF_REQUIRE(d->grid_size > 0.f, GF_ERR_INVALID_ARG, "splat: grid_size must be > 0 for fused host prep");
@@ -119,7 +126,7 @@ int gf_abi_version(void) { return GF_ABI_VERSION; }
 
 const char *gf_last_error(void) { return g_err; }
 
-int gf_splat_set_render_events(void *before, void *after) {
+int gf_debug_set_render_events(void *before, void *after) {
     g_ev_before = static_cast<cudaEvent_t>(before);
     g_ev_after = static_cast<cudaEvent_t>(after);
     return GF_OK;
@@ -138,6 +145,12 @@ size_t gf_splat_forward_workspace_bytes(const gf_splat_desc *desc) {
     return ws.bytes;
 }
 
+int gf_splat_ce_partials(const gf_splat_desc *desc) {
+    if (check_desc(desc) != GF_OK) return 0;
+    if (static_cast<long long>(desc->N) != static_cast<long long>(desc->H) * desc->W * desc->D) return 0;
+    return render_ctas_per_sample(*desc) * batch_of(*desc);
+}
+
 size_t gf_splat_backward_workspace_bytes(const gf_splat_desc *desc) {
     if (check_desc(desc) != GF_OK) return 0;
     return backward_workspace_bytes(*desc);
@@ -149,7 +162,12 @@ int gf_splat_forward(const gf_splat_desc *desc, const gf_splat_inputs *in, const
     if (rc != GF_OK) return rc;
     rc = check_inputs(desc, in);
     if (rc != GF_OK) return rc;
-    GF_REQUIRE(out != nullptr && (desc->N == 0 || out->logits != nullptr), GF_ERR_INVALID_ARG, "splat: logits is NULL");
+    GF_REQUIRE(out != nullptr && (desc->N == 0 || out->logits || out->logits_cn || out->argmax || out->ce_partials),
+               GF_ERR_INVALID_ARG, "splat: no output requested (logits, logits_cn, argmax and ce_partials are all NULL)");
+    const bool tile_path = static_cast<long long>(desc->N) == static_cast<long long>(desc->H) * desc->W * desc->D;
+    if (out->ce_partials)
+        GF_REQUIRE(out->labels != nullptr && tile_path, GF_ERR_INVALID_ARG,
+                   "splat: ce_partials needs labels and one point per voxel (N == H*W*D)");
     if (desc->variant == GF_SPLAT_PROB && desc->N > 0)
         GF_REQUIRE(out->bin_logits && out->density && out->probability, GF_ERR_INVALID_ARG,
                    "splat(prob): bin_logits / density / probability must not be NULL");
@@ -163,12 +181,12 @@ int gf_splat_forward(const gf_splat_desc *desc, const gf_splat_inputs *in, const
     int num_sms = 1;
     rc = num_sms_of_current_device(&num_sms);
     if (rc != GF_OK) return rc;
-    if (desc->N == 0) return GF_OK;
     // The tile path needs exactly one point per voxel in x-major order; it verifies that on the
     // device and hands over to the generic kernel otherwise.  N != H*W*D can only be generic.
-    const bool tile_path = static_cast<long long>(desc->N) == static_cast<long long>(desc->H) * desc->W * desc->D;
+    // (The preparation kernels run for N == 0 too: they initialise the status word gf_splat_read_flags reports.)
     rc = launch_prep(*desc, *in, ws, tile_path ? 0u : GF_FLAG_GENERIC_PATH, stream);
     if (rc != GF_OK) return rc;
+    if (desc->N == 0) return GF_OK;
     return launch_render(*desc, *in, *out, ws, tile_path, num_sms, stream);
 }
 
@@ -180,8 +198,14 @@ int gf_splat_backward(const gf_splat_desc *desc, const gf_splat_inputs *in, cons
     if (rc != GF_OK) return rc;
     GF_REQUIRE(gr != nullptr, GF_ERR_INVALID_ARG, "splat backward: grads struct is NULL");
     if (desc->G == 0) return GF_OK;
-    GF_REQUIRE(gr->means_grad && gr->opacity_grad && gr->semantics_grad && gr->cov_grad, GF_ERR_INVALID_ARG,
+    GF_REQUIRE(gr->means_grad && gr->opacity_grad && gr->semantics_grad, GF_ERR_INVALID_ARG,
                "splat backward: output gradient pointers must not be NULL");
+    if (in->cov)
+        GF_REQUIRE(gr->cov_grad != nullptr, GF_ERR_INVALID_ARG, "splat backward: cov_grad is NULL");
+    else
+        GF_REQUIRE(gr->scales_grad && gr->rotations_grad, GF_ERR_INVALID_ARG,
+                   "splat backward: scales_grad / rotations_grad must not be NULL when the inverse covariance is "
+                   "built from scales + rotations");
     if (desc->N > 0) {
         GF_REQUIRE(gr->logits_grad != nullptr, GF_ERR_INVALID_ARG, "splat backward: logits_grad is NULL");
         if (desc->variant == GF_SPLAT_PROB)
@@ -207,6 +231,8 @@ int gf_splat_read_flags(const void *workspace, gf_stream_t stream_, uint32_t *ho
     return GF_OK;
 }
 
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 static int check_daf(const gf_daf_desc *d) {
     GF_REQUIRE(d != nullptr, GF_ERR_INVALID_ARG, "daf: desc is NULL");
     GF_REQUIRE(d->batch >= 0 && d->num_pts >= 0 && d->num_cams > 0 && d->num_feat > 0 && d->num_embeds > 0 &&
@@ -223,6 +249,8 @@ int gf_daf_forward(const gf_daf_desc *desc, const float *feat, const int32_t *sh
     if (rc != GF_OK) return rc;
     if (static_cast<long long>(desc->batch) * desc->num_pts == 0) return GF_OK;
     GF_REQUIRE(feat && shape && start && loc && weights && output, GF_ERR_INVALID_ARG, "daf forward: NULL pointer");
+    GF_REQUIRE(aligned16(feat) && aligned16(output), GF_ERR_INVALID_ARG,
+               "daf forward: mc_ms_feat and output must be 16-byte aligned (the kernels use 16-byte vector accesses)");
     int num_sms = 1;
     rc = num_sms_of_current_device(&num_sms);
     if (rc != GF_OK) return rc;
@@ -238,6 +266,8 @@ int gf_daf_backward(const gf_daf_desc *desc, const float *feat, const int32_t *s
     if (static_cast<long long>(desc->batch) * desc->num_pts == 0) return GF_OK;
     GF_REQUIRE(feat && shape && start && loc && weights && grad_output && grad_feat && grad_loc && grad_weights,
                GF_ERR_INVALID_ARG, "daf backward: NULL pointer");
+    GF_REQUIRE(aligned16(feat) && aligned16(grad_output) && aligned16(grad_feat), GF_ERR_INVALID_ARG,
+               "daf backward: mc_ms_feat, grad_output and grad_mc_ms_feat must be 16-byte aligned");
     int num_sms = 1;
     rc = num_sms_of_current_device(&num_sms);
     if (rc != GF_OK) return rc;
@@ -271,6 +301,8 @@ int gf_daf_fused_forward(const gf_daf_fused_desc *fd, const float *feat, const i
     if (static_cast<long long>(fd->d.batch) * fd->d.num_pts == 0) return GF_OK;
     GF_REQUIRE(feat && shape && start && loc && logits && output && stats, GF_ERR_INVALID_ARG,
                "daf fused forward: NULL pointer");
+    GF_REQUIRE(aligned16(feat) && aligned16(output), GF_ERR_INVALID_ARG,
+               "daf fused forward: mc_ms_feat and output must be 16-byte aligned");
     int num_sms = 1;
     rc = num_sms_of_current_device(&num_sms);
     if (rc != GF_OK) return rc;
@@ -288,6 +320,8 @@ int gf_daf_fused_backward(const gf_daf_fused_desc *fd, const float *feat, const 
     GF_REQUIRE(feat && shape && start && loc && logits && stats && output && grad_output && grad_feat && grad_loc &&
                    grad_logits,
                GF_ERR_INVALID_ARG, "daf fused backward: NULL pointer");
+    GF_REQUIRE(aligned16(feat) && aligned16(output) && aligned16(grad_output) && aligned16(grad_feat), GF_ERR_INVALID_ARG,
+               "daf fused backward: mc_ms_feat, output, grad_output and grad_mc_ms_feat must be 16-byte aligned");
     int num_sms = 1;
     rc = num_sms_of_current_device(&num_sms);
     if (rc != GF_OK) return rc;
@@ -308,6 +342,9 @@ int gf_daf_format(const gf_daf_format_desc *desc, float *const *maps, float *tab
         rows += desc->hw[l];
     }
     GF_REQUIRE(rows < (1ll << 31), GF_ERR_UNSUPPORTED, "daf format: too many rows");
+    GF_REQUIRE(aligned16(table), GF_ERR_INVALID_ARG, "daf format: table must be 16-byte aligned");
+    for (int l = 0; l < desc->num_scale; ++l)
+        GF_REQUIRE(aligned16(maps[l]), GF_ERR_INVALID_ARG, "daf format: map %d must be 16-byte aligned", l);
     return gf::launch_daf_format(*desc, maps, table, inverse != 0, static_cast<cudaStream_t>(stream_));
 }
 

@@ -62,9 +62,12 @@ struct SplatWorkspace {
     int st;                // supertile edge (columns)
     int nsx, nsy, nsuper;  // supertile grid
     int nwords;            // ceil(G/32)
-    int pack_ctas;
+    int pack_ctas;         // pack CTAs per sample
+    int batch;             // samples; every region above except `flags` holds `batch` consecutive per-sample blocks
     size_t bytes;
 };
+
+__host__ __device__ inline int batch_of(const gf_splat_desc &d) { return d.batch > 0 ? d.batch : 1; }
 
 constexpr int kPackThreads = 64;   // small CTAs: ~400 of them cover the 148 SMs several times over
 
@@ -203,6 +206,99 @@ __device__ __forceinline__ bool gaussian_box(const gf_splat_desc &d, const gf_sp
         if (l > dims[a] - 1 || h < 0 || lo[a] > hi[a]) empty = true;
     }
     return empty;
+}
+
+// ---- batch: the tensors of sample b (dense strides; NULL stays NULL; pts may be shared by the batch) ----------------
+template <class T>
+__device__ __forceinline__ T *adv(T *p, long long off) { return p ? p + off : p; }
+
+__device__ __forceinline__ gf_splat_inputs sample_inputs(const gf_splat_desc &d, const gf_splat_inputs &in, int b) {
+    gf_splat_inputs o;
+    const long long G = d.G, N = d.N;
+    const long long np = d.pts_shared ? 0 : b * N * 3;
+    o.pts = adv(in.pts, np);
+    o.points_int = adv(in.points_int, np);
+    o.means = adv(in.means, b * G * 3);
+    o.means_int = adv(in.means_int, b * G * 3);
+    o.opacities = adv(in.opacities, b * G);
+    o.semantics = adv(in.semantics, b * G * d.C);
+    o.cov = adv(in.cov, b * G * d.cov_stride);
+    o.radii = adv(in.radii, b * G * (d.radii_axes == 3 ? 3 : 1));
+    o.scales = adv(in.scales, b * G * 3);
+    o.rotations = adv(in.rotations, b * G * 4);
+    return o;
+}
+
+__device__ __forceinline__ gf_splat_outputs sample_outputs(const gf_splat_desc &d, const gf_splat_outputs &out, int b, int ce_rows) {
+    gf_splat_outputs o;
+    const long long N = d.N;
+    o.logits = adv(out.logits, b * N * d.C);
+    o.bin_logits = adv(out.bin_logits, b * N);
+    o.density = adv(out.density, b * N);
+    o.probability = adv(out.probability, b * N);
+    o.argmax = adv(out.argmax, b * N);
+    o.logits_cn = adv(out.logits_cn, b * N * d.C);
+    o.labels = adv(out.labels, b * N);
+    o.class_weights = out.class_weights;
+    o.ce_partials = adv(out.ce_partials, 2ll * b * ce_rows);
+    return o;
+}
+
+__device__ __forceinline__ gf_splat_grads sample_grads(const gf_splat_desc &d, const gf_splat_grads &gr, int b) {
+    gf_splat_grads o;
+    const long long G = d.G, N = d.N;
+    o.logits_grad = adv(gr.logits_grad, b * N * d.C);
+    o.bin_logits_grad = adv(gr.bin_logits_grad, b * N);
+    o.density_grad = adv(gr.density_grad, b * N);
+    o.logits = adv(gr.logits, b * N * d.C);
+    o.bin_logits = adv(gr.bin_logits, b * N);
+    o.probability = adv(gr.probability, b * N);
+    o.means_grad = adv(gr.means_grad, b * G * 3);
+    o.opacity_grad = adv(gr.opacity_grad, b * G);
+    o.semantics_grad = adv(gr.semantics_grad, b * G * d.C);
+    o.cov_grad = adv(gr.cov_grad, b * G * d.cov_stride);
+    o.scales_grad = adv(gr.scales_grad, b * G * 3);
+    o.rotations_grad = adv(gr.rotations_grad, b * G * 4);
+    return o;
+}
+
+// Rotation matrix of the NORMALISED quaternion (w,x,y,z) -- get_rotation_matrix, model/utils/utils.py:20-66
+// (F.normalize: q / max(|q|, 1e-12)).  R[k][l], row-major.
+__device__ __forceinline__ void quat_rotation(const float q[4], float R[3][3], float &inv_norm) {
+    const float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    inv_norm = __fdiv_rn(1.f, fmaxf(n, 1e-12f));
+    const float w = q[0] * inv_norm, x = q[1] * inv_norm, y = q[2] * inv_norm, z = q[3] * inv_norm;
+    R[0][0] = w * w + x * x - y * y - z * z; R[0][1] = 2.f * (x * y - w * z);         R[0][2] = 2.f * (x * z + w * y);
+    R[1][0] = 2.f * (x * y + w * z);         R[1][1] = w * w - x * x + y * y - z * z; R[1][2] = 2.f * (y * z - w * x);
+    R[2][0] = 2.f * (x * z - w * y);         R[2][1] = 2.f * (y * z + w * x);         R[2][2] = w * w - x * x - y * y + z * z;
+}
+
+// Sigma^-1 = R^T diag(1/s^2) R as (xx,yy,zz,xy,yz,xz): the closed form of GaussianHead.prepare_gaussian_args'
+// Cov = (S R)^T (S R); Cov.cpu().inverse() (model/head/gaussian_head.py:111-119), R orthogonal.
+__device__ __forceinline__ void cov6_from_srt(const float s[3], const float q[4], float c6[6]) {
+    float R[3][3], inv_norm;
+    quat_rotation(q, R, inv_norm);
+    const float d0 = __fdiv_rn(1.f, s[0] * s[0]), d1 = __fdiv_rn(1.f, s[1] * s[1]), d2 = __fdiv_rn(1.f, s[2] * s[2]);
+    auto a = [&](int i, int j) { return R[0][i] * d0 * R[0][j] + R[1][i] * d1 * R[1][j] + R[2][i] * d2 * R[2][j]; };
+    c6[0] = a(0, 0); c6[1] = a(1, 1); c6[2] = a(2, 2); c6[3] = a(0, 1); c6[4] = a(1, 2); c6[5] = a(0, 2);
+}
+
+// the six inverse-covariance entries (xx,yy,zz,xy,yz,xz) of Gaussian g (in: the tensors of ONE sample)
+__device__ __forceinline__ void load_cov6_in(const gf_splat_desc &d, const gf_splat_inputs &in, int g, float c6[6]) {
+    if (in.cov == nullptr) {
+        const float s[3] = {__ldg(in.scales + 3 * g), __ldg(in.scales + 3 * g + 1), __ldg(in.scales + 3 * g + 2)};
+        const float q[4] = {__ldg(in.rotations + 4 * g), __ldg(in.rotations + 4 * g + 1), __ldg(in.rotations + 4 * g + 2),
+                            __ldg(in.rotations + 4 * g + 3)};
+        cov6_from_srt(s, q, c6);
+        return;
+    }
+    const float *cv = in.cov + static_cast<size_t>(g) * d.cov_stride;
+    if (d.cov_stride == 9) {  // flat entries [0,4,8,1,5,2] of the row-major 3x3 (__init__.py:143)
+        c6[0] = __ldg(cv); c6[1] = __ldg(cv + 4); c6[2] = __ldg(cv + 8); c6[3] = __ldg(cv + 1); c6[4] = __ldg(cv + 5); c6[5] = __ldg(cv + 2);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) c6[i] = __ldg(cv + i);
+    }
 }
 
 // the six inverse-covariance entries (xx,yy,zz,xy,yz,xz) of Gaussian g

@@ -40,12 +40,30 @@ struct BwdParams {
     int chunk;         // box voxels per chunk
     int32_t *canon;    // non-zero after voxel_map_kernel iff N == H*W*D and point n sits in voxel n for all n
     float4 *aux;       // [N] prob only: per-point terms that do not depend on the Gaussian
+    size_t cv_block;   // bytes between the (canon, v2p) blocks of consecutive samples
 };
 
-__global__ void __launch_bounds__(256) voxel_map_kernel(const BwdParams p) {
+// The launch parameters narrowed to sample b of the batch (the kernels run with blockIdx.y = sample).
+__device__ __forceinline__ BwdParams sample_bwd(const BwdParams &p, int b) {
+    BwdParams q = p;
+    q.in = sample_inputs(p.d, p.in, b);
+    q.gr = sample_grads(p.d, p.gr, b);
+    q.canon = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(p.canon) + b * p.cv_block);
+    q.v2p = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(p.v2p) + b * p.cv_block);
+    q.big = p.big + static_cast<size_t>(b) * p.d.G;
+    q.big_ctr = p.big_ctr + b;
+    q.aux = adv(p.aux, static_cast<long long>(b) * p.d.N);
+    return q;
+}
+
+__global__ void __launch_bounds__(256) voxel_map_kernel(const BwdParams pb) {
     pdl_launch_dependents();   // the pair kernels may become resident; they wait before using the map
-    if (blockIdx.x == 0 && threadIdx.x == 0) *p.big_ctr = 0ull;
+    const BwdParams p = sample_bwd(pb, blockIdx.y);
     const int H = p.d.H, W = p.d.W, D = p.d.D;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *p.big_ctr = 0ull;
+        if (static_cast<long long>(p.d.N) != static_cast<long long>(H) * W * D) *p.canon = 0;   // can only be generic
+    }
     for (long long n = blockIdx.x * 256ll + threadIdx.x; n < p.d.N; n += 256ll * gridDim.x) {
         int ix, iy, iz;
         if (p.in.points_int) {
@@ -68,8 +86,9 @@ __global__ void __launch_bounds__(256) voxel_map_kernel(const BwdParams p) {
 //   y = (1 - bin_logits[n]) * dL/dbin[n]
 //   z = dL/ddensity[n]
 //   w = 1 / probability[n]  if probability[n] > 1e-9 else 0   (0 switches the logits branch off)
-__global__ void __launch_bounds__(256) prob_aux_kernel(const BwdParams p, int C) {
+__global__ void __launch_bounds__(256) prob_aux_kernel(const BwdParams pb, int C) {
     pdl_launch_dependents();
+    const BwdParams p = sample_bwd(pb, blockIdx.y);
     for (long long n = blockIdx.x * 256ll + threadIdx.x; n < p.d.N; n += 256ll * gridDim.x) {
         float x = 0.f;
         for (int k = 0; k < C; ++k) x = fmaf(__ldg(p.gr.logits_grad + n * C + k), __ldg(p.gr.logits + n * C + k), x);
@@ -128,7 +147,7 @@ struct GaussAcc {
 #pragma unroll
         for (int a = 0; a < 3; ++a) mu[a] = p.in.means[3 * g + a];
         float c6[6];
-        load_cov6(p.d, p.in.cov, g, c6);
+        load_cov6_in(p.d, p.in, g, c6);
         q6[0] = -0.5f * kLog2e * c6[0]; q6[1] = -0.5f * kLog2e * c6[1]; q6[2] = -0.5f * kLog2e * c6[2];
         q6[3] = -kLog2e * c6[3]; q6[4] = -kLog2e * c6[4]; q6[5] = -kLog2e * c6[5];
         opa = p.in.opacities[g];
@@ -294,7 +313,7 @@ __device__ __forceinline__ void finish(const BwdParams &p, int g, float v, int l
     const float s0 = __shfl_sync(0xffffffffu, v, 0), s1 = __shfl_sync(0xffffffffu, v, 1), s2 = __shfl_sync(0xffffffffu, v, 2);
     const float sg = PROB ? __shfl_sync(0xffffffffu, v, 10 + C) : 0.f;
     float c6[6];
-    load_cov6(p.d, p.in.cov, g, c6);
+    load_cov6_in(p.d, p.in, g, c6);
     const float a = c6[0], b = c6[1], c = c6[2], d = c6[3], e = c6[4], f = c6[5];
     float out = 0.f;
     float *dst = nullptr;   // lane >= 10 + C: nothing to store
@@ -418,8 +437,9 @@ __device__ __forceinline__ void walk_pairs(const BwdParams &p, GaussAcc<C, PROB>
 }
 
 template <int C, bool PROB>
-__global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_small_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_small_kernel(const BwdParams pb) {
     constexpr int kBwdThreads = bwd_threads(PROB);
+    const BwdParams p = sample_bwd(pb, blockIdx.y);
     const int lane = threadIdx.x & 31;
     // no early exit for the warps past G: they redo the last Gaussian and skip the stores, which keeps
     // every warp provably converged at the shuffles below
@@ -455,8 +475,9 @@ __global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_sm
 }
 
 template <int C, bool PROB>
-__global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_big_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_big_kernel(const BwdParams pb) {
     constexpr int kBwdThreads = bwd_threads(PROB);
+    const BwdParams p = sample_bwd(pb, blockIdx.y);
     pdl_wait();
     const unsigned long long ctr = *p.big_ctr;
     const int nbig = static_cast<int>(ctr >> 40);
@@ -503,6 +524,46 @@ __global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_bi
     }
 }
 
+// Gradients of the fused pre-op (in.cov == NULL): the [G,6] gradient of Sigma^-1 = R^T diag(1/s^2) R mapped to the
+// scales and the (un-normalised) quaternion.  With U the upper-triangular matrix of the six gradients (only the six
+// gathered entries of the 3x3 carry gradient, __init__.py:143) and Gs = U + U^T:
+//   dL/dD_k = 1/2 r_k^T Gs r_k (r_k = row k of R),  dL/ds_k = -2/s_k^3 dL/dD_k,  dL/dR_kl = D_k (Gs r_k)_l,
+// then through the quaternion -> matrix map (model/utils/utils.py:20-66) and F.normalize.
+__global__ void __launch_bounds__(128) srt_grad_kernel(const BwdParams pb) {
+    pdl_wait();
+    const BwdParams p = sample_bwd(pb, blockIdx.y);
+    const int g = blockIdx.x * 128 + threadIdx.x;
+    if (g >= p.d.G) return;
+    const float *g6 = p.gr.cov_grad + 6 * static_cast<size_t>(g);
+    const float s[3] = {p.in.scales[3 * g], p.in.scales[3 * g + 1], p.in.scales[3 * g + 2]};
+    const float q[4] = {p.in.rotations[4 * g], p.in.rotations[4 * g + 1], p.in.rotations[4 * g + 2], p.in.rotations[4 * g + 3]};
+    float R[3][3], inv_norm;
+    quat_rotation(q, R, inv_norm);
+    const float Gs[3][3] = {{2.f * g6[0], g6[3], g6[5]}, {g6[3], 2.f * g6[1], g6[4]}, {g6[5], g6[4], 2.f * g6[2]}};
+    float M[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float Dk = __fdiv_rn(1.f, s[k] * s[k]);
+        float t[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) t[l] = Gs[l][0] * R[k][0] + Gs[l][1] * R[k][1] + Gs[l][2] * R[k][2];
+        const float dD = 0.5f * (R[k][0] * t[0] + R[k][1] * t[1] + R[k][2] * t[2]);
+        p.gr.scales_grad[3 * g + k] = -2.f * dD * __fdiv_rn(Dk, s[k]);
+#pragma unroll
+        for (int l = 0; l < 3; ++l) M[k][l] = Dk * t[l];
+    }
+    const float w = q[0] * inv_norm, x = q[1] * inv_norm, y = q[2] * inv_norm, z = q[3] * inv_norm;
+    const float gw = 2.f * (w * (M[0][0] + M[1][1] + M[2][2]) - z * M[0][1] + y * M[0][2] + z * M[1][0] - x * M[1][2] - y * M[2][0] + x * M[2][1]);
+    const float gx = 2.f * (x * (M[0][0] - M[1][1] - M[2][2]) + y * M[0][1] + z * M[0][2] + y * M[1][0] - w * M[1][2] + z * M[2][0] + w * M[2][1]);
+    const float gy = 2.f * (y * (-M[0][0] + M[1][1] - M[2][2]) + x * M[0][1] + w * M[0][2] + x * M[1][0] + z * M[1][2] - w * M[2][0] + z * M[2][1]);
+    const float gz = 2.f * (z * (-M[0][0] - M[1][1] + M[2][2]) - w * M[0][1] + x * M[0][2] + w * M[1][0] + y * M[1][2] + x * M[2][0] + y * M[2][1]);
+    const float dot = w * gw + x * gx + y * gy + z * gz;
+    p.gr.rotations_grad[4 * g] = inv_norm * (gw - w * dot);
+    p.gr.rotations_grad[4 * g + 1] = inv_norm * (gx - x * dot);
+    p.gr.rotations_grad[4 * g + 2] = inv_norm * (gy - y * dot);
+    p.gr.rotations_grad[4 * g + 3] = inv_norm * (gz - z * dot);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -511,6 +572,9 @@ struct BwdWorkspace {
     unsigned long long *big_ctr;
     uint2 *big;
     float4 *aux;
+    float *cov6;       // [B,G,6] gradient of Sigma^-1 when the caller passed scales + rotations instead of cov
+    size_t cv_block;   // bytes of one sample's (canon word, voxel -> point map) block
+    size_t cv_bytes;   // all of them: one memset
     size_t bytes;
 };
 
@@ -528,16 +592,21 @@ static size_t align_up_b(size_t v, size_t a) { return (v + a - 1) / a * a; }
 void plan_backward_workspace(const gf_splat_desc &d, void *base, BwdWorkspace *ws) {
     size_t off = 0;
     char *b = static_cast<char *>(base);
+    const size_t B = static_cast<size_t>(batch_of(d));
     auto take = [&](size_t bytes) {
         char *p = b ? b + off : nullptr;
         off = align_up_b(off + bytes, 256);
         return p;
     };
-    ws->big_ctr = reinterpret_cast<unsigned long long *>(take(64));
-    ws->canon = reinterpret_cast<int32_t *>(take(256));   // directly in front of v2p: one memset covers both
-    ws->v2p = reinterpret_cast<int32_t *>(take(size_t(d.H) * d.W * d.D * 4));
-    ws->big = reinterpret_cast<uint2 *>(take(size_t(d.G) * sizeof(uint2)));
-    ws->aux = reinterpret_cast<float4 *>(take(d.variant == GF_SPLAT_PROB ? size_t(d.N) * 16 : 0));
+    ws->big_ctr = reinterpret_cast<unsigned long long *>(take(B * 8));
+    // per sample: the canon word (256 bytes) directly in front of its voxel -> point map; one memset covers all
+    ws->cv_block = 256 + align_up_b(size_t(d.H) * d.W * d.D * 4, 256);
+    ws->cv_bytes = B * ws->cv_block;
+    ws->canon = reinterpret_cast<int32_t *>(take(ws->cv_bytes));
+    ws->v2p = ws->canon ? ws->canon + 64 : nullptr;
+    ws->big = reinterpret_cast<uint2 *>(take(B * size_t(d.G) * sizeof(uint2)));
+    ws->aux = reinterpret_cast<float4 *>(take(d.variant == GF_SPLAT_PROB ? B * size_t(d.N) * 16 : 0));
+    ws->cov6 = reinterpret_cast<float *>(take(B * size_t(d.G) * 6 * 4));   // only used with scales + rotations input
     ws->bytes = off;
 }
 
@@ -548,19 +617,19 @@ size_t backward_workspace_bytes(const gf_splat_desc &d) {
 }
 
 template <int C, bool PROB>
-static int launch_backward_t(const BwdParams &bp, int num_sms, cudaStream_t stream) {
+static int launch_backward_t(const BwdParams &bp, const BwdWorkspace &ws, bool srt, int num_sms, cudaStream_t stream) {
     const gf_splat_desc &d = bp.d;
-    // canon word (non-zero = "still canonical") and the voxel->point map (-1 = empty) in one fill
-    GF_CUDA_TRY(cudaMemsetAsync(bp.canon, 0xFF, 256 + size_t(d.H) * d.W * d.D * 4, stream));
-    if (static_cast<long long>(d.N) != static_cast<long long>(d.H) * d.W * d.D)
-        GF_CUDA_TRY(cudaMemsetAsync(bp.canon, 0, 4, stream));
+    const int B = batch_of(d);
+    GF_REQUIRE(B <= 65535, GF_ERR_UNSUPPORTED, "splat backward: batch above 65535");
+    // canon words (non-zero = "still canonical") and the voxel->point maps (-1 = empty) in one fill
+    GF_CUDA_TRY(cudaMemsetAsync(bp.canon, 0xFF, ws.cv_bytes, stream));
     const long long want = (static_cast<long long>(d.N) + 255) / 256;
     const int grid0 = static_cast<int>(want < 16ll * num_sms ? (want > 0 ? want : 1) : 16ll * num_sms);
-    voxel_map_kernel<<<grid0, 256, 0, stream>>>(bp);   // plain stream order: never overlaps the previous call
+    voxel_map_kernel<<<dim3(grid0, B), 256, 0, stream>>>(bp);   // plain stream order: never overlaps the previous call
     GF_CUDA_TRY(cudaGetLastError());
     if (PROB) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid0); cfg.blockDim = dim3(256); cfg.stream = stream;
+        cfg.gridDim = dim3(grid0, B); cfg.blockDim = dim3(256); cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -569,8 +638,11 @@ static int launch_backward_t(const BwdParams &bp, int num_sms, cudaStream_t stre
     }
     constexpr int kBwdThreads = bwd_threads(PROB);
     const int per_cta = kBwdThreads / 32;
-    GF_CUDA_TRY(launch_chained(backward_small_kernel<C, PROB>, dim3((d.G + per_cta - 1) / per_cta), dim3(kBwdThreads), 0, stream, bp));
-    GF_CUDA_TRY(launch_chained(backward_big_kernel<C, PROB>, dim3(num_sms * bwd_ctas(PROB) * 2), dim3(kBwdThreads), 0, stream, bp));
+    GF_CUDA_TRY(launch_chained(backward_small_kernel<C, PROB>, dim3((d.G + per_cta - 1) / per_cta, B), dim3(kBwdThreads), 0, stream, bp));
+    int big_ctas = (num_sms * bwd_ctas(PROB) * 2 + B - 1) / B;   // per sample: together they fill the GPU twice over
+    if (big_ctas < 32) big_ctas = 32;
+    GF_CUDA_TRY(launch_chained(backward_big_kernel<C, PROB>, dim3(big_ctas, B), dim3(kBwdThreads), 0, stream, bp));
+    if (srt) GF_CUDA_TRY(launch_chained(srt_grad_kernel, dim3((d.G + 127) / 128, B), dim3(128), 0, stream, bp));
     return GF_OK;
 }
 
@@ -582,17 +654,23 @@ int launch_backward(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_
     bp.d = d;
     bp.in = in;
     bp.gr = gr;
+    const bool srt = in.cov == nullptr;
+    if (srt) {   // the pair kernels write the [G,6] gradient of Sigma^-1 into the workspace; srt_grad_kernel maps it on
+        bp.d.cov_stride = 6;
+        bp.gr.cov_grad = ws.cov6;
+    }
     bp.v2p = ws.v2p;
     bp.big = ws.big;
     bp.big_ctr = ws.big_ctr;
     bp.chunk = chunk_voxels(d);
     bp.canon = ws.canon;
     bp.aux = ws.aux;
+    bp.cv_block = ws.cv_block;
     const bool prob = d.variant == GF_SPLAT_PROB;
-#define GF_CASE(CC)                                                       \
-    case CC:                                                              \
-        return prob ? launch_backward_t<CC, true>(bp, num_sms, stream)    \
-                    : launch_backward_t<CC, false>(bp, num_sms, stream);
+#define GF_CASE(CC)                                                                \
+    case CC:                                                                       \
+        return prob ? launch_backward_t<CC, true>(bp, ws, srt, num_sms, stream)    \
+                    : launch_backward_t<CC, false>(bp, ws, srt, num_sms, stream);
     switch (d.C) {
         GF_CASE(16)
         GF_CASE(17)

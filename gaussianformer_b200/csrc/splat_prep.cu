@@ -38,6 +38,12 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
     const int g = blockIdx.x * kPackThreads + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool live = g < p.d.G;
+    // sample b of the batch: its input tensors and its blocks of the workspace regions
+    const int b = blockIdx.y;
+    const gf_splat_inputs in = sample_inputs(p.d, p.in, b);
+    float *const records = p.records + static_cast<size_t>(b) * p.d.G * p.rec;
+    PackedBox *const boxes = p.boxes + static_cast<size_t>(b) * p.d.G;
+    uint32_t *const masks = p.masks + static_cast<size_t>(b) * p.nsx * p.nsy * p.nwords;
     if (threadIdx.x == 0) s_err = 0;
     pdl_launch_dependents();   // the list kernel may become resident now; it waits for this grid before reading
 
@@ -46,34 +52,25 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
     bool empty = true;
     if (live) {
         // ---- every load first (read-only path), then arithmetic, then stores ------------------------
-        const float mu[3] = {__ldg(p.in.means + 3 * g), __ldg(p.in.means + 3 * g + 1), __ldg(p.in.means + 3 * g + 2)};
+        const float mu[3] = {__ldg(in.means + 3 * g), __ldg(in.means + 3 * g + 1), __ldg(in.means + 3 * g + 2)};
         float c6[6];
-        {
-            const float *cv = p.in.cov + static_cast<size_t>(g) * p.d.cov_stride;
-            if (p.d.cov_stride == 9) {  // flat entries [0,4,8,1,5,2] of the row-major 3x3 (__init__.py:143)
-                c6[0] = __ldg(cv); c6[1] = __ldg(cv + 4); c6[2] = __ldg(cv + 8);
-                c6[3] = __ldg(cv + 1); c6[4] = __ldg(cv + 5); c6[5] = __ldg(cv + 2);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) c6[i] = __ldg(cv + i);
-            }
-        }
-        float amp = __ldg(p.in.opacities + g);
+        load_cov6_in(p.d, in, g, c6);   // the caller's Sigma^-1, or R^T diag(1/s^2) R from scales + rotations (cov == NULL)
+        float amp = __ldg(in.opacities + g);
         const int nq = (p.rec - kGeomFloats) / 4;   // <= 5 for C <= 20
         float semv[20];
         {
-            const float *sem = p.in.semantics + static_cast<size_t>(g) * p.d.C;
+            const float *sem = in.semantics + static_cast<size_t>(g) * p.d.C;
 #pragma unroll
             for (int i = 0; i < 20; ++i) semv[i] = (i < p.d.C) ? __ldg(sem + i) : 0.f;
         }
-        empty = gaussian_box(p.d, p.in, g, mu, lo, hi, err);
+        empty = gaussian_box(p.d, in, g, mu, lo, hi, err);
 
-        PackedBox b;
-        b.x = empty ? 1u : (static_cast<uint32_t>(lo[0]) | static_cast<uint32_t>(hi[0]) << 16);
-        b.y = empty ? 1u : (static_cast<uint32_t>(lo[1]) | static_cast<uint32_t>(hi[1]) << 16);
-        b.z = empty ? 1u : (static_cast<uint32_t>(lo[2]) | static_cast<uint32_t>(hi[2]) << 16);
-        b.empty = empty ? 1u : 0u;
-        p.boxes[g] = b;
+        PackedBox bx;
+        bx.x = empty ? 1u : (static_cast<uint32_t>(lo[0]) | static_cast<uint32_t>(hi[0]) << 16);
+        bx.y = empty ? 1u : (static_cast<uint32_t>(lo[1]) | static_cast<uint32_t>(hi[1]) << 16);
+        bx.z = empty ? 1u : (static_cast<uint32_t>(lo[2]) | static_cast<uint32_t>(hi[2]) << 16);
+        bx.empty = empty ? 1u : 0u;
+        boxes[g] = bx;
 
         const float a_ = c6[0], b_ = c6[1], c_ = c6[2], d_ = c6[3], e_ = c6[4], f_ = c6[5];
         if (p.d.variant == GF_SPLAT_PROB) {
@@ -86,7 +83,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
 #pragma unroll
             for (int i = 0; i < 20; ++i) semv[i] *= amp;
         }
-        float4 *rec = reinterpret_cast<float4 *>(p.records + static_cast<size_t>(g) * p.rec);
+        float4 *rec = reinterpret_cast<float4 *>(records + static_cast<size_t>(g) * p.rec);
         rec[0] = make_float4(mu[0], mu[1], mu[2], amp);
         rec[1] = make_float4(-0.5f * kLog2e * a_, -0.5f * kLog2e * b_, -0.5f * kLog2e * c_, -kLog2e * d_);
         rec[2] = make_float4(-kLog2e * e_, -kLog2e * f_, 0.f, 0.f);
@@ -128,7 +125,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
             }
             __syncwarp();
             for (int i = lane; i < npass; i += 32)
-                p.masks[static_cast<size_t>(base + i) * p.nwords + word] = s_mask[warp][i];
+                masks[static_cast<size_t>(base + i) * p.nwords + word] = s_mask[warp][i];
             __syncwarp();
         }
     }
@@ -137,7 +134,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
     __syncthreads();
     if (err) atomicOr(&s_err, err);
     __syncthreads();
-    if (threadIdx.x == 0) p.pack_flags[blockIdx.x] = s_err;
+    if (threadIdx.x == 0) p.pack_flags[blockIdx.y * gridDim.x + blockIdx.x] = s_err;
 }
 
 struct ListParams {
@@ -148,7 +145,7 @@ struct ListParams {
     uint32_t *flags;
     int nwords;
     int G;
-    int pack_ctas;
+    int pack_ctas;   // pack CTAs of the whole batch
     uint32_t initial_flags;
 };
 
@@ -156,7 +153,7 @@ constexpr int kListThreads = 256;
 constexpr int kListWordsPerThread = 4;   // consecutive mask words per thread and pass (keeps ascending order)
 
 __global__ void __launch_bounds__(kListThreads) list_kernel(const ListParams p) {
-    const int s = blockIdx.x;
+    const int s = blockIdx.y * gridDim.x + blockIdx.x;   // supertile blockIdx.x of sample blockIdx.y
     const uint32_t *words = p.masks + static_cast<size_t>(s) * p.nwords;
     int32_t *list = p.lists + static_cast<size_t>(s) * p.G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -212,6 +209,7 @@ __global__ void __launch_bounds__(kListThreads) list_kernel(const ListParams p) 
         if (lane == 0 && e) atomicOr(&s_e, e);
         __syncthreads();
         if (threadIdx.x == 0) p.flags[0] = s_e;
+        else if (threadIdx.x < 16) p.flags[threadIdx.x] = 0u;   // words 4..11: cycle counters of a GF_RENDER_TIMING build
     }
 }
 
@@ -241,6 +239,8 @@ int plan_forward_workspace(const gf_splat_desc &d, void *base, SplatWorkspace *w
     ws->nsuper = ws->nsx * ws->nsy;
     ws->nwords = (d.G + 31) / 32;
     ws->pack_ctas = (d.G + kPackThreads - 1) / kPackThreads;
+    const size_t B = static_cast<size_t>(batch_of(d));
+    ws->batch = static_cast<int>(B);
     size_t off = 0;
     char *b = static_cast<char *>(base);
     auto take = [&](size_t bytes) {
@@ -249,12 +249,12 @@ int plan_forward_workspace(const gf_splat_desc &d, void *base, SplatWorkspace *w
         return p;
     };
     ws->flags = reinterpret_cast<uint32_t *>(take(64));
-    ws->pack_flags = reinterpret_cast<uint32_t *>(take(size_t(ws->pack_ctas) * 4));
-    ws->records = reinterpret_cast<float *>(take(size_t(d.G) * rec_floats(d.C) * 4));
-    ws->boxes = reinterpret_cast<PackedBox *>(take(size_t(d.G) * sizeof(PackedBox)));
-    ws->masks = reinterpret_cast<uint32_t *>(take(size_t(ws->nsuper) * ws->nwords * 4));
-    ws->lists = reinterpret_cast<int32_t *>(take(size_t(ws->nsuper) * d.G * 4));
-    ws->counts = reinterpret_cast<int32_t *>(take(size_t(ws->nsuper) * 4));
+    ws->pack_flags = reinterpret_cast<uint32_t *>(take(B * size_t(ws->pack_ctas) * 4));
+    ws->records = reinterpret_cast<float *>(take(B * size_t(d.G) * rec_floats(d.C) * 4));
+    ws->boxes = reinterpret_cast<PackedBox *>(take(B * size_t(d.G) * sizeof(PackedBox)));
+    ws->masks = reinterpret_cast<uint32_t *>(take(B * size_t(ws->nsuper) * ws->nwords * 4));
+    ws->lists = reinterpret_cast<int32_t *>(take(B * size_t(ws->nsuper) * d.G * 4));
+    ws->counts = reinterpret_cast<int32_t *>(take(B * size_t(ws->nsuper) * 4));
     ws->bytes = off;
     return GF_OK;
 }
@@ -274,7 +274,7 @@ int launch_prep(const gf_splat_desc &d, const gf_splat_inputs &in, const SplatWo
     pp.nsy = ws.nsy;
     pp.nwords = ws.nwords;
     if (ws.pack_ctas > 0) {
-        pack_mask_kernel<<<ws.pack_ctas, kPackThreads, 0, stream>>>(pp);
+        pack_mask_kernel<<<dim3(ws.pack_ctas, ws.batch), kPackThreads, 0, stream>>>(pp);
         GF_CUDA_TRY(cudaGetLastError());
     }
     ListParams lp;
@@ -285,9 +285,10 @@ int launch_prep(const gf_splat_desc &d, const gf_splat_inputs &in, const SplatWo
     lp.flags = ws.flags;
     lp.nwords = ws.nwords;
     lp.G = d.G;
-    lp.pack_ctas = ws.pack_ctas;
+    lp.pack_ctas = ws.pack_ctas * ws.batch;
     lp.initial_flags = initial_flags;
-    GF_CUDA_TRY(launch_chained(list_kernel, dim3(ws.nsuper), dim3(kListThreads), 0, stream, lp));
+    GF_REQUIRE(ws.batch <= 65535, GF_ERR_UNSUPPORTED, "splat: batch above 65535");
+    GF_CUDA_TRY(launch_chained(list_kernel, dim3(ws.nsuper, ws.batch), dim3(kListThreads), 0, stream, lp));
     return GF_OK;
 }
 

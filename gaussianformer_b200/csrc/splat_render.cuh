@@ -19,7 +19,32 @@ struct RenderParams {
     int st, nsy;     // supertile edge, supertiles along y
     int nby;         // bins along y
     int nzc;         // z chunks
+    int nbx;         // bins along x (blockIdx.z = sample * nbx + bin x)
+    int nsuper;      // supertiles per sample
+    int ce_rows;     // rows of out.ce_partials per sample (= render CTAs per sample)
+    int vec_ok;      // D % 4 == 0 and every tensor the tile kernel touches with 16-byte vectors is 16-byte aligned
 };
+
+// The launch parameters narrowed to sample b of the batch: per-sample input tensors and workspace blocks.  The output
+// pointers are narrowed separately (with_sample_outputs) where they are needed, i.e. after the accumulation loop,
+// so that they do not occupy registers during it.
+__device__ __forceinline__ RenderParams with_sample_outputs(const RenderParams &p, const RenderParams &launch, int b) {
+    RenderParams q = p;
+    q.out = sample_outputs(launch.d, launch.out, b, launch.ce_rows);
+    return q;
+}
+__device__ __forceinline__ RenderParams sample_params(const RenderParams &p, int b) {
+    RenderParams q = p;
+    const long long G = p.d.G;
+    const long long np = p.d.pts_shared ? 0 : static_cast<long long>(b) * p.d.N * 3;
+    q.pts = p.pts + np;
+    q.points_int = adv(p.points_int, np);
+    q.records = p.records + static_cast<size_t>(b) * G * rec_floats(p.d.C);
+    q.boxes = p.boxes + static_cast<size_t>(b) * G;
+    q.lists = p.lists + static_cast<size_t>(b) * p.nsuper * G;
+    q.counts = p.counts + static_cast<size_t>(b) * p.nsuper;
+    return q;
+}
 
 // index of the largest of C values, lowest index on ties
 template <int C>
@@ -107,7 +132,10 @@ __device__ __forceinline__ void render_one_point(const RenderParams &p, long lon
         p.out.probability[n] = zsum;
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) p.out.logits[n * C + c] = acc[c];
+    for (int c = 0; c < C; ++c) {
+        if (p.out.logits) p.out.logits[n * C + c] = acc[c];
+        if (p.out.logits_cn) p.out.logits_cn[static_cast<long long>(c) * p.d.N + n] = acc[c];
+    }
     if (p.out.argmax) p.out.argmax[n] = static_cast<uint8_t>(argmax_of<C>(acc));
 }
 

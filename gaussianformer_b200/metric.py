@@ -22,8 +22,10 @@ class MeanIoU:
         self.total_positive = torch.zeros_like(self.total_seen)
 
     def after_step(self, outputs, targets, mask=None):
-        if self.total_seen.device != outputs.device:
-            self.reset(outputs.device)
+        if self.total_seen.device != outputs.device:   # keep what was accumulated: move the counters, never wipe them
+            self.total_seen = self.total_seen.to(outputs.device)
+            self.total_correct = self.total_correct.to(outputs.device)
+            self.total_positive = self.total_positive.to(outputs.device)
         if mask is not None:
             outputs, targets = outputs[mask], targets[mask]
         for i, c in enumerate(self.class_indices):

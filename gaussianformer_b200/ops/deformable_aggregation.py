@@ -33,13 +33,19 @@ def _desc(feat, spatial_shape, sampling_location, weights):
     return d
 
 
+def _a16(t):
+    """The kernels read / write / atomically add 16-byte vectors: a tensor whose storage offset leaves it misaligned
+    (a slice of a larger buffer) is copied to a fresh allocation; the C ABI rejects misaligned pointers."""
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
 def _normalise(mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights):
     for t in (mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights):
         if not t.is_cuda:
             raise RuntimeError("DeformableAggregationFunction is CUDA-only (sm_100a); there is no CPU fallback.")
-    return (mc_ms_feat.contiguous().float(), spatial_shape.contiguous().int(),
-            scale_start_index.contiguous().int(), sampling_location.contiguous().float(),
-            weights.contiguous().float())
+    return (_a16(mc_ms_feat.contiguous().float()), spatial_shape.contiguous().int(),
+            scale_start_index.contiguous().int(), _a16(sampling_location.contiguous().float()),
+            _a16(weights.contiguous().float()))
 
 
 def _format_call(maps, table, channels, inverse):
@@ -78,7 +84,7 @@ class _FeatureMapsToTable(Function):
 
     @staticmethod
     def forward(ctx, *maps):
-        maps = [fm.contiguous() for fm in maps]
+        maps = [_a16(fm.contiguous()) for fm in maps]
         bs, num_cams, channels = maps[0].shape[:3]
         ctx.shapes = [tuple(fm.shape) for fm in maps]
         total = sum(fm.shape[-2] * fm.shape[-1] for fm in maps)
@@ -89,7 +95,7 @@ class _FeatureMapsToTable(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_table):
-        grad_table = grad_table.contiguous().float()
+        grad_table = _a16(grad_table.contiguous().float())
         grads = [torch.empty(shape, dtype=torch.float32, device=grad_table.device) for shape in ctx.shapes]
         _format_call(grads, grad_table, ctx.shapes[0][2], True)
         return tuple(grads)
@@ -147,7 +153,7 @@ class DeformableAggregationFunction(Function):
         mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights = ctx.saved_tensors
         d = _desc(mc_ms_feat, spatial_shape, sampling_location, weights)
         dev = mc_ms_feat.device
-        grad_output = grad_output.contiguous().float()
+        grad_output = _a16(grad_output.contiguous().float())
         with torch.cuda.device(dev):
             grad_feat = torch.zeros_like(mc_ms_feat)
             grad_loc = torch.zeros_like(sampling_location)
@@ -216,7 +222,7 @@ class DeformableAggregationFusedFunction(Function):
         point_mask = rest.pop(0) if ctx.has_masks[0] else None
         weight_mask = rest.pop(0) if ctx.has_masks[1] else None
         dev = mc_ms_feat.device
-        grad_output = grad_output.contiguous().float()
+        grad_output = _a16(grad_output.contiguous().float())
         with torch.cuda.device(dev):
             grad_feat = torch.zeros_like(mc_ms_feat)
             grad_loc = torch.zeros_like(sampling_location)

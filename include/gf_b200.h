@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define GF_ABI_VERSION 1
+#define GF_ABI_VERSION 2
 
 /* status codes */
 #define GF_OK 0
@@ -80,6 +80,12 @@ typedef struct gf_splat_desc {
     float grid_size;
     float scale_multiplier;
     int32_t radii_min;  /* <=0: no clamp (base variant); >=1: radii.clamp(min) (prob variants) */
+    /* ---- ABI 2: explicit batch (the reference op is per sample, local_aggregate/__init__.py:128) ---- */
+    int32_t batch;      /* samples per call, B >= 1 (0 is read as 1).  Every input / output / gradient tensor carries a
+                           leading dimension B with dense strides ([B,N,3], [B,G,3], [B,G], [B,G,C], [B,N,C], ...); all B
+                           samples are processed by ONE grid per kernel, and the workspace is B times the B = 1 size */
+    int32_t pts_shared; /* != 0: pts / points_int are ONE [N,3] array shared by every sample of the batch (the voxel
+                           centres of the occupancy grid, dataset/transform_3d.py:487-499) instead of [B,N,3] */
 } gf_splat_desc;
 
 /* Inputs of both passes.  points_int / means_int / radii mirror the reference's native
@@ -94,17 +100,33 @@ typedef struct gf_splat_inputs {
     const float *semantics;   /* [G,C] */
     const float *cov;         /* [G,cov_stride] inverse covariance */
     const int32_t *radii;     /* [G] or [G,3], or NULL */
-    const float *scales;      /* [G,3]; only read when radii == NULL */
+    const float *scales;      /* [G,3]; read when radii == NULL or cov == NULL */
+    /* ---- ABI 2: head pre-op fusion ---- */
+    const float *rotations;   /* [G,4] quaternions (w,x,y,z), any norm > 0, or NULL.  With cov == NULL the inverse
+                                 covariance is built on the device as R^T diag(1/s^2) R from scales and rotations -- the
+                                 closed form of GaussianHead.prepare_gaussian_args' Cov = (S R)^T (S R),
+                                 Cov.cpu().inverse().cuda() (model/head/gaussian_head.py:111-119; quaternion -> matrix
+                                 as model/utils/utils.py:20-66) -- inside the pack kernel */
 } gf_splat_inputs;
 
 typedef struct gf_splat_outputs {
-    float *logits;      /* [N,C] */
+    float *logits;      /* [N,C]; may be NULL when logits_cn, argmax or ce_partials is requested instead */
     float *bin_logits;  /* [N]  (prob only) */
     float *density;     /* [N]  (prob only) */
     float *probability; /* [N]  (prob only; saved for backward like the reference) */
     uint8_t *argmax;    /* [N]  optional, NULL = off: class with the largest logit per point (lowest
                            index on ties) — the `argmax(dim=1)` of GaussianHead.forward
                            (model/head/gaussian_head.py:185) fused into the render epilogue */
+    /* ---- ABI 2: post-op fusion toward the loss; all optional, NULL = off ---- */
+    float *logits_cn;   /* [C,N] per sample: the logits class-major, i.e. the `semantics[None].transpose(1, 2)` /
+                           `[1, C, N]` layout GaussianHead hands to the loss (gaussian_head.py:165-175), written by the
+                           render epilogue; `logits` may then be NULL (inference: the [N,C] copy never exists) */
+    const uint8_t *labels;      /* [N] per sample: target class per point, 255 = ignore (loss/occupancy_loss.py:113-127) */
+    const float *class_weights; /* [C] (shared by the batch) or NULL = all ones */
+    float *ce_partials; /* [gf_splat_ce_partials(desc), 2] fully overwritten: per render CTA (sum_n w[y_n] * nll_n,
+                           sum_n w[y_n]) of CE_ssc_loss = nn.CrossEntropyLoss(weight, ignore_index=255, 'mean')
+                           (loss/occupancy_loss.py:164-178) over the CTA's points; loss = sum(col 0) / sum(col 1).
+                           Needs labels; tile path only (N == H*W*D, canonical order) */
 } gf_splat_outputs;
 
 typedef struct gf_splat_grads {
@@ -121,7 +143,11 @@ typedef struct gf_splat_grads {
     float *opacity_grad;          /* [G] */
     float *semantics_grad;        /* [G,C] */
     float *cov_grad;              /* cov_stride 6: [G,6] in (xx,yy,zz,xy,yz,xz) order; cov_stride 9: [G,9] row-major
-                                     3x3, entries [0,4,8,1,5,2] carry the gradient, [3,6,7] are written as 0 */
+                                     3x3, entries [0,4,8,1,5,2] carry the gradient, [3,6,7] are written as 0.
+                                     May be NULL when in->cov == NULL (scales + rotations input) */
+    /* ---- ABI 2: gradients of the fused pre-op (in->cov == NULL, in->rotations != NULL); fully overwritten ---- */
+    float *scales_grad;           /* [G,3] through Sigma^-1 only (the radii are detached, __init__.py:134) */
+    float *rotations_grad;        /* [G,4] w.r.t. the un-normalised quaternion */
 } gf_splat_grads;
 
 typedef struct gf_daf_desc {
@@ -155,6 +181,8 @@ const char *gf_last_error(void);
 int gf_splat_supported_classes(int32_t *out, int cap);
 
 size_t gf_splat_forward_workspace_bytes(const gf_splat_desc *desc);
+/* rows of out->ce_partials for this desc (render CTAs of the tile path x batch); 0 when the tile path does not apply */
+int gf_splat_ce_partials(const gf_splat_desc *desc);
 size_t gf_splat_backward_workspace_bytes(const gf_splat_desc *desc);
 
 int gf_splat_forward(const gf_splat_desc *desc, const gf_splat_inputs *in,
@@ -169,12 +197,6 @@ int gf_splat_backward(const gf_splat_desc *desc, const gf_splat_inputs *in,
  * (GF_FLAG_* bits) and synchronises the stream.  The reference raises AssertionError from Python
  * for the same conditions. */
 int gf_splat_read_flags(const void *workspace, gf_stream_t stream, uint32_t *host_flags);
-
-/* Measurement aid for bench.py's roofline line: when both events are non-NULL (cudaEvent_t created
- * with timing enabled), every following gf_splat_forward on this thread records them on its stream
- * immediately before / after the tile render kernel, so that kernel can be timed alone inside a
- * normal run.  Pass NULLs to switch it off.  Not part of the reference boundary. */
-int gf_splat_set_render_events(void *before, void *after);
 
 /* out[B,P,C] is fully overwritten. */
 int gf_daf_forward(const gf_daf_desc *desc, const float *mc_ms_feat, const int32_t *spatial_shape,

@@ -10,8 +10,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _header_functions():
-    src = open(os.path.join(ROOT, "include", "gf_b200.h")).read()
+def _header_functions(name="gf_b200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(gf_[a-z0-9_]+)\s*\(", src)))
 
@@ -23,9 +23,11 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     names = _header_functions()
     assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
-    for n in names:
+    debug = _header_functions("gf_b200_debug.h")          # measurement hooks live in their own header
+    assert set(debug) == set(_lib.DEBUG_EXPORTS), (debug, _lib.DEBUG_EXPORTS)
+    for n in names + debug:
         assert hasattr(L, n), n
-    assert L.gf_abi_version() == 1
+    assert L.gf_abi_version() == 2
 
 
 def test_struct_layouts_follow_the_header():

@@ -24,6 +24,7 @@ def test_native_boundary_inputs_match_fused_prep():
     (logits, _, _, _), ws = splat_forward_raw(desc, T(a["pts"]), T(a["means"]), T(a["opa"]), T(a["sem"]), T(cov6),
                                               points_int=T(pi, torch.int32), means_int=T(mi, torch.int32),
                                               radii=T(radii, torch.int32))
+    logits = logits[0]                                  # leading batch dimension of the batched ABI (B = 1)
     ref = h.oracle_forward(kw, inp, variant)
     h.assert_close(logits.cpu().numpy(), ref["logits"], what="native-boundary logits")
     # and the module path (fused prep, cov 3x3) gives bit-identical output
@@ -32,9 +33,9 @@ def test_native_boundary_inputs_match_fused_prep():
     out = m(t["pts"], t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
     assert torch.equal(out, logits)
     g = torch.randn(N, 18, generator=torch.Generator().manual_seed(3)).to(dev)
-    gm, go, gs, gc = splat_backward_raw(desc, T(a["pts"]), T(a["means"]), T(a["opa"]), T(a["sem"]), T(cov6),
-                                        (g, None, None), (None, None, None), points_int=T(pi, torch.int32),
-                                        means_int=T(mi, torch.int32), radii=T(radii, torch.int32))
+    gm, go, gs, gc, _, _ = (None if x is None else x[0] for x in splat_backward_raw(
+        desc, T(a["pts"]), T(a["means"]), T(a["opa"]), T(a["sem"]), T(cov6), (g, None, None), (None, None, None),
+        points_int=T(pi, torch.int32), means_int=T(mi, torch.int32), radii=T(radii, torch.int32)))
     rm, ro, rs, rc = h.oracle_backward(kw, inp, variant, (g.cpu().numpy(),))
     for name, mine, r in (("means", gm, rm), ("opa", go, ro), ("sem", gs, rs), ("cov", gc, rc)):
         h.assert_close(mine.cpu().numpy(), r, rtol=1e-3, atol=h.grad_tolerance(r), what="native grad " + name)
@@ -54,3 +55,20 @@ def test_status_codes():
     rc = L.gf_splat_forward(ctypes.byref(d), ctypes.byref(ins), ctypes.byref(outs), ctypes.c_void_p(t.data_ptr()), 16, None)
     assert rc == 2                                                                        # GF_ERR_WORKSPACE
     assert 18 in _lib.supported_classes()
+    assert L.gf_abi_version() == 2
+
+
+def test_zero_points_still_initialises_the_status_word():
+    """N == 0: nothing is rendered, but the preparation kernels run, so gf_splat_read_flags reports the Gaussian
+    error bits instead of uninitialised memory."""
+    from gaussianformer_b200.splat import read_flags
+    G = 40
+    gen = torch.Generator().manual_seed(0)
+    means = (torch.rand(G, 3, generator=gen) * 4).cuda()
+    means[3, 0] = 1e3                                   # outside the 8x8x8 grid
+    d = _make_desc(G, 0, 18, 8, 8, 8, _lib.GF_SPLAT_BASE, 1, 6, (0.0, 0.0, 0.0), 0.5, 3.0, 0)
+    cov6 = torch.tensor([[4.0, 4.0, 4.0, 0.0, 0.0, 0.0]]).repeat(G, 1).cuda()
+    scales = torch.full((G, 3), 0.3).cuda()
+    (_lg, _, _, _), ws = splat_forward_raw(d, torch.zeros(0, 3).cuda(), means, torch.ones(G).cuda(),
+                                           torch.rand(G, 18, generator=gen).cuda(), cov6, scales=scales)
+    assert read_flags(ws, ws.device) & _lib.GF_FLAG_MEAN_OUT_OF_GRID

@@ -3,7 +3,7 @@
 # tools/build_variant.py), optionally ncu captures.  Usage (through gpurun):
 #   bash tools/gpu_round.sh <tag> "<variants>" [tests] [ncu] [full]
 # A variant is `default`, the name of a library built by tools/build_variant.py (e.g. `pipe2` after
-# `python tools/build_variant.py pipe2 -DGF_TILE_PIPE=2`), `render:<x>` for GF_B200_RENDER=<x> (tc, tc2, tc3), `st:<n>` for GF_B200_ST=<n>, and `<selector>@<library>` combines
+# `python tools/build_variant.py pipe2 -DGF_TILE_PIPE=2`), `st:<n>` for GF_B200_ST=<n>, and `<selector>@<library>` combines
 # an environment selector with a variant library (e.g. `render:tc3@tc3half` after
 # `python tools/build_variant.py tc3half -DGF_TC3_HALF=1`).
 # Every non-default variant first runs the splat parity tests, then two bench lines.
@@ -24,12 +24,11 @@ for v in $variants; do
   # a variant is <selector>[@<library>]: selector = default | render:<x> | st:<n> | <library>
   sel=${v%%@*}; lib=""
   if [ "$sel" != "$v" ]; then lib=${v#*@}; fi
-  if [ ${sel:0:7} = render: ]; then export GF_B200_RENDER=${sel:7};      # e.g. render:tc3, render:tc2, render:tc
-  elif [ ${sel:0:3} = st: ]; then export GF_B200_ST=${sel:3};            # supertile edge, e.g. st:8
+  if [ ${sel:0:3} = st: ]; then export GF_B200_ST=${sel:3};            # supertile edge, e.g. st:8
   elif [ $sel != default ]; then lib=$sel; fi
   if [ -n "$lib" ]; then export GF_B200_LIB=$PWD/gaussianformer_b200/csrc/variants/libgf_b200_$lib.so; fi
   if [ $v != default ]; then
-    timeout 600 python -m pytest tests/test_splat_gpu.py tests/test_cabi_gpu.py -m gpu -x -q 2>&1 | tail -1 | sed "s/^/$v parity: /"
+    timeout 600 python -m pytest tests/test_splat_gpu.py tests/test_cabi_gpu.py tests/test_batch_fused_gpu.py -m gpu -x -q 2>&1 | tail -1 | sed "s/^/$v parity: /"
   fi
   for rep in 1 2; do
     timeout 300 python bench.py --steps 200 --warmup 20 --no-extras > $out/bench_${v}_$rep.json 2> $out/bench_${v}_$rep.err

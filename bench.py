@@ -3,22 +3,26 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step is one forward pass of the splat op (pack + supertile lists + render; 3 kernel launches)
-over one synthetic sample of BASELINE.json configs[1]: `nuscenes_gs25600_solid.py` shape —
-25 600 Gaussians (+ the "empty" Gaussian) into the 200x200x16 grid, 18 classes, batch 1 per GPU.
-Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md "Measurement".
+A step is one forward pass of the splat op (pack + supertile lists + render; 3 kernel launches, replayed from a CUDA
+graph) over one synthetic sample of BASELINE.json configs[1]: `nuscenes_gs25600_solid.py` shape — 25 600 Gaussians
+(+ the "empty" Gaussian) into the 200x200x16 grid, 18 classes, batch 1 per GPU.  Prints ONE JSON line (rank 0).
+Keys follow the driver contract; see DESIGN.md "Measurement".
 
 * value        whole-job Gaussians/s with inputs resident in HBM, CUDA-event timed, max over ranks
-* e2e          the same metric through the public module (`local_aggregate.LocalAggregator`) with
-               HOST (pinned) inputs: H2D of every input + forward (logits + fused arg-max) + D2H of
-               the occupancy prediction inside the timed region
-* roofline     the tile render kernel timed alone (events recorded around it inside the C ABI),
-               algorithmic bytes 112*G + 84*N   over the measured HBM copy peak
+* e2e          the same metric through the drop-in module call `local_aggregate.LocalAggregator.forward` with HOST
+               (pinned) inputs: H2D of every input + forward + arg-max + D2H of the occupancy prediction inside the
+               timed region; `h2d_floor_ms` is the plain pinned copy of the same bytes on the same box
+* roofline     the tile render kernel timed alone (events recorded around it inside the C ABI, debug header),
+               algorithmic bytes 112*G + 84*N over the measured HBM copy peak; `roofline_cfg3` is the
+               same figure for BASELINE config 3 (144 000 Gaussians)
+* fwd_bwd      BASELINE config 5: forward + backward at 4 samples per GPU in ONE batched launch per kernel, one scalar
+               loss all-reduce per step
+* prob         BASELINE config 4: probabilistic head, 6 400 Gaussians, 2 samples per GPU (bs 4 over 2 GPUs), both roofs
 * cpu_baseline the oracle's C/OpenMP port of the reference algorithm on the host cores (rank 0)
 
-`--impl reference` times that CPU port as the reference arm (the reference has no CPU
-implementation of the splat; its CUDA op cannot run without a GPU build of torch extensions —
-when oracle/_ref was shipped, its timing on this GPU is reported as `ref_cuda_op` in the main line).
+`--impl reference` times that CPU port as the reference arm (the reference has no CPU implementation of the splat; its
+CUDA op cannot run without a GPU build of torch extensions — when oracle/_ref was shipped, its timing on this GPU is
+reported as `ref_cuda_op` in the main line).  It always runs on ONE host CPU (rank 0), whatever --gpus says.
 """
 from __future__ import annotations
 
@@ -38,10 +42,25 @@ METRIC = "gaussians_to_voxels_per_sec"
 UNIT = "Gaussians/s"
 G_COUNTED = 25600                 # learned Gaussians per sample (the empty one is overhead)
 N_SETS = 6                        # rotating input/output sets so the working set exceeds L2
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # CUDA-core fp32 roof of a B200: 148 SMs x 128 FMA lanes x 2 x 1.965 GHz
 
 
-def _algorithmic_bytes(G, N, C=18):
-    return (3 + 6 + 1 + C) * 4 * G + 12 * N + 4 * C * N      # 112*G + 84*N for C = 18
+def _algorithmic_bytes(G, N, C=18, prob=False):
+    # inputs read once + outputs written once.  base 112*G + 84*N, prob 112*G + 96*N (C = 18)
+    return (3 + 6 + 1 + C) * 4 * G + 12 * N + 4 * (C + (3 if prob else 0)) * N
+
+
+def _algorithmic_bytes_bwd(G, N, C=18, prob=False):
+    # base 224*G + 84*N, prob 224*G + 172*N
+    return 2 * (3 + 6 + 1 + C) * 4 * G + 12 * N + (4 * (2 * C + 4) * N if prob else 4 * C * N)
+
+
+def _config(world, perturb):
+    """The `config` object of the JSON line — the SAME dict for both arms (the driver compares them)."""
+    return {"workload": f"{WORKLOAD}: 25600 Gaussians (+1 empty) -> 200x200x16x18 voxels, batch 1 per GPU, points = "
+                        + ("perturbed voxel centres" if perturb else "voxel centres (BASELINE.md §3)"),
+            "l2": f"{N_SETS} rotating input/output/workspace sets (> 126 MB L2)",
+            "parallelism": f"dp{world} (one sample per GPU, scalar loss all-reduce)"}
 
 
 class ClockSampler(threading.Thread):
@@ -107,7 +126,6 @@ def _measured_peak():
 
 def _cpu_port_once(kw, inp):
     """One forward of the CPU port (oracle C code, all OpenMP threads).  Returns seconds."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle
     a = {k: v[0].numpy() for k, v in inp.items()}
     dims = (kw["H"], kw["W"], kw["D"])
@@ -124,26 +142,38 @@ def _cpu_port_once(kw, inp):
 _LAST_PORT = {}   # logits / (voxel, Gaussian) pair count of the most recent CPU-port forward (checker side figures)
 
 
+def _all_host_threads():
+    """Give the CPU port every core this process may run on, whatever OMP_NUM_THREADS a launcher (torchrun sets 1)
+    exported.  Returns the thread count in effect."""
+    import oracle
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return oracle.set_num_threads(n)
+
+
 def run_reference_arm(args):
-    """Reference arm: the reference algorithm's CPU port on this box's host cores (rank 0 only)."""
+    """Reference arm: the reference algorithm's CPU port on this box's host cores.  ONE host CPU at any --gpus:
+    under torchrun rank 0 alone runs and prints it, the other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
     from gaussianformer_b200.synthetic import make_splat_inputs
-    kw, inp, _ = make_splat_inputs(WORKLOAD, seed=0, perturb=False)
-    for _ in range(max(1, min(args.warmup, 2))):
+    cores = _all_host_threads()
+    kw, inp, _ = make_splat_inputs(WORKLOAD, seed=0, perturb=args.perturb)
+    for _ in range(min(max(args.warmup, 1), 3)):       # the port has no clocks or caches to warm beyond a few passes
         _cpu_port_once(kw, inp)
-    steps = max(1, min(args.steps, 10))
+    steps = max(1, args.steps)
     t = [_cpu_port_once(kw, inp) for _ in range(steps)]
     sec = sum(t) / len(t)
     value = G_COUNTED / sec
-    cores = oracle.num_threads()
-    sample = f"{steps} full forward passes of the {WORKLOAD} sample (N=640000 points, G=25601)"
+    sample = (f"{steps} full forward passes of the {WORKLOAD} sample (N=640000 points, G=25601), {sec:.3f} s each; "
+              f"one host CPU ({cores} OpenMP threads) regardless of --gpus")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD}: 25600 Gaussians (+1 empty) -> 200x200x16x18, batch 1"},
+            "config": _config(args.gpus, args.perturb),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -155,7 +185,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (bwd, prob, DAF, ref op)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (bwd, DAF, ref op) and the config 3/4/5 legs")
+    ap.add_argument("--no-graph", action="store_true", help="launch the three kernels of a step directly instead of replaying a CUDA graph")
     ap.add_argument("--perturb", action="store_true", help="jitter every point inside its voxel (LoadOccupancySurroundOcc(perturb=True)); "
                     "the shipped configs and BASELINE.md use exact voxel centres")
     args = ap.parse_args()
@@ -199,7 +230,6 @@ def main():
     outs = [torch.empty((N, C), device=dev) for _ in range(N_SETS)]
     wss = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in range(N_SETS)]
     stream = torch.cuda.current_stream(dev)
-    sptr = ctypes.c_void_p(stream.cuda_stream)
     calls = []
     for t, o, w in zip(sets, outs, wss):
         ins = _lib.SplatInputs(_ptr(t["pts"]), None, _ptr(t["means"]), None, _ptr(t["opa"]), _ptr(t["sem"]),
@@ -209,9 +239,36 @@ def main():
     loss_buf = torch.zeros(1, device=dev)
     pending = []
 
-    def step(i):
+    def direct_call(i, s):
         ins, ou, w = calls[i % N_SETS]
-        _lib.check(L.gf_splat_forward(ctypes.byref(desc), ctypes.byref(ins), ctypes.byref(ou), _ptr(w), ws_bytes, sptr))
+        _lib.check(L.gf_splat_forward(ctypes.byref(desc), ctypes.byref(ins), ctypes.byref(ou), _ptr(w), ws_bytes,
+                                      ctypes.c_void_p(s.cuda_stream)))
+
+    # One CUDA graph per resident set: pack -> list -> render with their programmatic-dependent-launch edges, so that
+    # a step costs one graph launch and `value` does not depend on how fast the host issues three launches.
+    graphs = None
+    if not args.no_graph:
+        try:
+            for i in range(N_SETS):
+                direct_call(i, stream)                      # warm (module load, attribute caches) before capturing
+            torch.cuda.synchronize(dev)
+            graphs = []
+            cap_stream = torch.cuda.Stream(dev)
+            for i in range(N_SETS):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap_stream):
+                    direct_call(i, torch.cuda.current_stream(dev))
+                graphs.append(g)
+        except Exception as e:                              # fall back to direct launches, and say so
+            graphs = None
+            print(f"[bench] CUDA graph capture failed ({e!r}); using direct launches", file=sys.stderr)
+            torch.cuda.synchronize(dev)
+
+    def step(i):
+        if graphs is not None:
+            graphs[i % N_SETS].replay()
+        else:
+            direct_call(i, stream)
         if world > 1:
             # north star: NCCL only for the (scalar) loss all-reduce.  It is issued asynchronously on
             # NCCL's stream so that it overlaps the next sample's kernels; every handle is waited for
@@ -248,16 +305,20 @@ def main():
     value = world * G_COUNTED / (ms_per_step * 1e-3)
 
     # ---- roofline: the render kernel alone, events recorded around it inside the C ABI -----------
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 50))]
-    for i, (a, b) in enumerate(evs):
-        a.record(stream); b.record(stream)          # materialise the underlying cudaEvent_t
-        L.gf_debug_set_render_events(ctypes.c_void_p(a.cuda_event), ctypes.c_void_p(b.cuda_event))
-        step(i)
-    L.gf_debug_set_render_events(None, None)
-    torch.cuda.synchronize(dev)
-    render_ms = sorted(a.elapsed_time(b) for a, b in evs)
-    render_ms = sum(render_ms) / len(render_ms)
     peak, peak_kind = _measured_peak()
+
+    def render_alone(call, nrep):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nrep)]
+        for i, (a, b) in enumerate(evs):
+            a.record(stream); b.record(stream)          # materialise the underlying cudaEvent_t
+            L.gf_debug_set_render_events(ctypes.c_void_p(a.cuda_event), ctypes.c_void_p(b.cuda_event))
+            call(i)
+        L.gf_debug_set_render_events(None, None)
+        torch.cuda.synchronize(dev)
+        ms = sorted(a.elapsed_time(b) for a, b in evs)
+        return sum(ms) / len(ms)
+
+    render_ms = render_alone(lambda i: direct_call(i, stream), min(max(K, 10), 50))
     alg = _algorithmic_bytes(G, N, C)
     achieved = alg / (render_ms * 1e-3) / 1e9
     traffic = None
@@ -265,10 +326,10 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "render_tc_kernel<18,false>" if os.environ.get("GF_B200_RENDER", "")[:1] == "t" else "render_tile_kernel<18,false>", "kernel_ms": render_ms,
+                "traffic": traffic, "kernel": "render_tile_kernel<18,false>", "kernel_ms": render_ms,
                 "algorithmic_bytes": alg, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)"}
 
-    # ---- e2e: public module, HOST inputs: H2D + forward (logits + fused arg-max) + D2H every step ----
+    # ---- e2e: the drop-in module call, HOST inputs: H2D + forward + arg-max + D2H every step ----
     # Each sample's six input tensors live in ONE pinned staging buffer (what a collate function
     # would produce), so a step is one H2D copy, the module call, and one D2H copy of the occupancy
     # prediction.  The host consumes prediction i-1 while step i is in flight (two result buffers),
@@ -277,73 +338,111 @@ def main():
     module = LocalAggregator(**kw).to(dev)
     module.validate = False     # the D2H read of the prediction is the step's synchronisation point
     n_host = 3
-    layouts, host = [], []
-    for i in range(n_host):
-        inp = inp0 if i == 0 else make_splat_inputs(WORKLOAD, seed=rank * 100 + i, perturb=PERTURB)[1]
-        offs, off = {}, 0
-        for k, v in inp.items():
-            offs[k] = (off, v.numel(), tuple(v.shape))
-            off += (v.numel() + 63) // 64 * 64          # 256-byte aligned slices
-        buf = torch.empty(off, dtype=torch.float32).pin_memory()
-        for k, v in inp.items():
-            o, nel, _ = offs[k]
-            buf[o:o + nel].copy_(v.reshape(-1))
-        layouts.append(offs)
-        host.append(buf)
-    h2d = host[0].numel() * 4
+
+    def stage(keys):
+        layouts, host = [], []
+        for i in range(n_host):
+            inp = inp0 if i == 0 else make_splat_inputs(WORKLOAD, seed=rank * 100 + i, perturb=PERTURB)[1]
+            offs, off = {}, 0
+            for k in keys:
+                v = inp[k]
+                offs[k] = (off, v.numel(), tuple(v.shape))
+                off += (v.numel() + 63) // 64 * 64          # 256-byte aligned slices
+            buf = torch.empty(off, dtype=torch.float32).pin_memory()
+            for k in keys:
+                o, nel, _ = offs[k]
+                buf[o:o + nel].copy_(inp[k].reshape(-1))
+            layouts.append(offs)
+            host.append(buf)
+        return layouts, host
+
     pred_host = [torch.empty(N, dtype=torch.uint8).pin_memory() for _ in range(2)]
     done = [torch.cuda.Event(), torch.cuda.Event()]
-    d2h = pred_host[0].numel()
     consumed = [0]
-
     copy_stream = torch.cuda.Stream(dev)
     h2d_done = [torch.cuda.Event() for _ in range(n_host)]
 
-    def e2e_step(i):
-        # the H2D copy of step i runs on a copy stream and overlaps the kernels of step i-1
-        with torch.cuda.stream(copy_stream):
-            dbuf = host[i % n_host].to(dev, non_blocking=True)
-            h2d_done[i % n_host].record(copy_stream)
-        stream.wait_event(h2d_done[i % n_host])
-        dbuf.record_stream(stream)
-        d = {k: dbuf[o:o + nel].view(shape) for k, (o, nel, shape) in layouts[i % n_host].items()}
-        _logits, occ = module.forward_with_occupancy(d["pts"], d["means"], d["opa"], d["sem"], d["scales"], d["cov"])
-        pred_host[i & 1].copy_(occ, non_blocking=True)
-        done[i & 1].record(stream)
+    def make_e2e_step(layouts, host, run):
+        def e2e_step(i):
+            # the H2D copy of step i runs on a copy stream and overlaps the kernels of step i-1
+            with torch.cuda.stream(copy_stream):
+                dbuf = host[i % n_host].to(dev, non_blocking=True)
+                h2d_done[i % n_host].record(copy_stream)
+            stream.wait_event(h2d_done[i % n_host])
+            dbuf.record_stream(stream)
+            d = {k: dbuf[o:o + nel].view(shape) for k, (o, nel, shape) in layouts[i % n_host].items()}
+            occ = run(d)
+            pred_host[i & 1].copy_(occ.reshape(-1), non_blocking=True)
+            done[i & 1].record(stream)
+            if world > 1:
+                pending.append(dist.all_reduce(loss_buf, async_op=True))
+            if i > 0:                                  # consume the previous step's prediction on the host
+                done[(i - 1) & 1].synchronize()
+                consumed[0] += int(pred_host[(i - 1) & 1][0])
+        return e2e_step
+
+    def run_e2e(e2e_step):
+        for i in range(4):
+            e2e_step(i)
+        steps = max(5, min(K, 100))
         if world > 1:
-            pending.append(dist.all_reduce(loss_buf, async_op=True))
-        if i > 0:                                  # consume the previous step's prediction on the host
-            done[(i - 1) & 1].synchronize()
-            consumed[0] += int(pred_host[(i - 1) & 1][0])
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        ms_dev = timed_region(steps, e2e_step)
+        wall = time.perf_counter() - t0
+        return max(ms_dev, 0.0) / steps, wall * 1e3 / steps
 
-    for i in range(4):
-        e2e_step(i)
-    e2e_steps = max(5, min(K, 100))
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    e2e_ms_dev = timed_region(e2e_steps, e2e_step)
-    e2e_wall = time.perf_counter() - t0
-    e2e_ms = max(e2e_ms_dev, 0.0) / e2e_steps
+    # (a) the reference-facing call: forward(pts, means, opa, sem, scales, cov) -> logits; arg-max as GaussianHead does
+    lay_a, host_a = stage(("pts", "means", "opa", "sem", "scales", "cov"))
+    step_a = make_e2e_step(lay_a, host_a, lambda d: module(d["pts"], d["means"], d["opa"], d["sem"], d["scales"], d["cov"]).argmax(dim=1).to(torch.uint8))
+    with torch.no_grad():
+        e2e_ms, e2e_wall = run_e2e(step_a)
+    h2d = host_a[0].numel() * 4
+    d2h = pred_host[0].numel()
+    # plain pinned copy of the same bytes on this box: what the PCIe / host path alone costs per step
+    with torch.cuda.stream(copy_stream):
+        for _ in range(3):
+            host_a[0].to(dev, non_blocking=True)
+        copy_stream.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(copy_stream)
+        for r in range(10):
+            host_a[r % n_host].to(dev, non_blocking=True)
+        c1.record(copy_stream)
+        copy_stream.synchronize()
+    h2d_floor_ms = c0.elapsed_time(c1) / 10
     e2e = {"value": world * G_COUNTED / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall * 1e3 / e2e_steps,
-           "host_numa_binding": numa,
-           "api": "local_aggregate.LocalAggregator.forward_with_occupancy (validate=False): one pinned staging "
-                  "buffer per sample -> H2D on a copy stream, logits + fused arg-max, D2H of the uint8 occupancy; "
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall,
+           "h2d_floor_ms": h2d_floor_ms, "host_numa_binding": numa,
+           "api": "local_aggregate.LocalAggregator.forward (drop-in signature, validate=False) + .argmax(1): one pinned "
+                  "staging buffer per sample -> H2D on a copy stream, forward, arg-max, D2H of the uint8 occupancy; "
                   "host reads prediction i-1 while step i runs"}
+    # (b) the grid-resident entry point: only the Gaussians travel (3.5 MB), arg-max fused into the render epilogue
+    lay_b, host_b = stage(("means", "opa", "sem", "scales", "cov"))
+    pts_grid = module.grid_points(dev)[0]
+    step_b = make_e2e_step(lay_b, host_b, lambda d: module.forward_eval(pts_grid, d["means"], d["opa"], d["sem"], d["scales"],
+                                                                        d["cov"], layout="nc")["final_occ"])
+    with torch.no_grad():
+        e2e_b_ms, _ = run_e2e(step_b)
+    e2e_on_grid = {"value": world * G_COUNTED / (e2e_b_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": host_b[0].numel() * 4,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": e2e_b_ms,
+                   "api": "LocalAggregator.forward_eval(pts = the grid's resident voxel centres, layout='nc'): logits + fused arg-max"}
 
+    legs = {}
+    if not args.no_extras:
+        legs = config_legs(dev, world, rank, timed_region, pending, loss_buf, render_alone, peak)
     extras = {}
     if rank == 0 and not args.no_extras:
         extras = side_measurements(dev, kw, inp0, sets[0], desc)
 
     cpu_baseline = None
     if rank == 0 and world == 1:
-        import oracle
+        cores = _all_host_threads()
         _cpu_port_once(kw, inp0)
         reps = [_cpu_port_once(kw, inp0) for _ in range(3)]
         sec = sum(reps) / len(reps)
-        cpu_baseline = {"value": G_COUNTED / sec, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+        cpu_baseline = {"value": G_COUNTED / sec, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"3 full forward passes of the {WORKLOAD} sample, {sec:.3f} s each (C/OpenMP oracle)"}
         try:
             # secondary, work-normalised figure: in-box (voxel, Gaussian) pairs per second and the fp32
@@ -366,25 +465,157 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{WORKLOAD}: 25600 Gaussians (+1 empty) -> 200x200x16x18 voxels, "
-                                       f"batch 1 per GPU, points = " + ("perturbed voxel centres" if PERTURB else "voxel centres (BASELINE.md §3)"),
-                           "l2": f"{N_SETS} rotating input/output/workspace sets "
-                                 f"({N_SETS * (alg + ws_bytes) / 1e6:.0f} MB) > 126 MB L2",
-                           "parallelism": f"dp{world} (one sample per GPU, scalar loss all-reduce)"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline,
+                "dtype": "f32", "data": "synthetic", "config": _config(world, PERTURB),
+                "launch": "CUDA graph replay (pack -> list -> render, PDL edges)" if graphs is not None else "3 direct launches per step",
+                "clocks": clocks, "e2e": e2e, "e2e_on_grid": e2e_on_grid, "gpu_launches": 3 * K, "roofline": roofline,
                 "cpu_baseline": cpu_baseline}
+        line.update(legs)
         line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def side_measurements(dev, kw, inp0, resident, desc):
-    """Reported next to the headline (not part of it): backward, prob variant, DAF, and the
-    reference CUDA op on the same GPU when oracle/_ref travelled with the repo."""
+def config_legs(dev, world, rank, timed_region, pending, loss_buf, render_alone, peak):
+    """BASELINE.json configs 3, 4 and 5 next to the headline (every rank takes part; rank 0 reports):
+    config 3: the 144 000-Gaussian forward, render kernel alone -> roofline_cfg3;
+    config 5: forward + backward, 4 samples per GPU in one batched launch per kernel, one scalar all-reduce per step;
+    config 4: probabilistic head, 2 samples per GPU (bs 4 over 2 GPUs), forward and backward, HBM and fp32 roofs."""
     import torch
-    from gaussianformer_b200.splat import LocalAggregator, LocalAggregatorProb
+    import torch.distributed as dist
+    from gaussianformer_b200 import _lib
+    from gaussianformer_b200.splat import LocalAggregator, LocalAggregatorProb, _make_desc, splat_forward_raw
+    from gaussianformer_b200.synthetic import make_splat_inputs
+    out = {}
+
+    def batch_inputs(name, seeds):
+        parts, kws = [], None
+        for s in seeds:
+            kws, inp, _ = make_splat_inputs(name, seed=s, perturb=False)
+            parts.append(inp)
+        return kws, {k: torch.cat([p[k] for p in parts], 0).to(dev).contiguous() for k in parts[0]}
+
+    def all_reduce_step():
+        if world > 1:
+            pending.append(dist.all_reduce(loss_buf, async_op=True))
+            if len(pending) > 8:
+                pending.pop(0).wait()
+
+    try:
+        # ---- config 3: gs144000 forward, render kernel alone ----
+        kw3, t3 = batch_inputs("gs144000", (rank * 100,))
+        G3, N3 = t3["means"].shape[1], t3["pts"].shape[1]
+        d3 = _make_desc(G3, N3, 18, kw3["H"], kw3["W"], kw3["D"], _lib.GF_SPLAT_BASE, 1, 9, kw3["pc_min"], kw3["grid_size"],
+                        float(kw3["scale_multiplier"]), 0, 1, 0)
+        cov3 = t3["cov"].reshape(1, G3, 9)
+
+        def call3(i):
+            splat_forward_raw(d3, t3["pts"], t3["means"], t3["opa"], t3["sem"], cov3, scales=t3["scales"])
+        for i in range(3):
+            call3(i)
+        k3 = render_alone(call3, 20)
+        fwd3 = timed_region(20, call3) / 20
+        alg3 = _algorithmic_bytes(G3, N3)
+        out["roofline_cfg3"] = {"bound": "hbm", "achieved": alg3 / (k3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": alg3 / (k3 * 1e-3) / 1e9 / peak, "kernel": "render_tile_kernel<18,false>",
+                                "kernel_ms": k3, "algorithmic_bytes": alg3, "op_call_ms": fwd3,
+                                "workload": "gs144000: 144000 Gaussians -> 200x200x16x18, batch 1"}
+        del t3, cov3
+    except Exception as e:
+        out["roofline_cfg3"] = {"error": repr(e)}
+
+    try:
+        # ---- config 5: forward + backward, 4 samples per GPU, one batched launch per kernel ----
+        B5 = 4
+        kw5, t5 = batch_inputs(WORKLOAD, tuple(rank * 100 + 10 + b for b in range(B5)))
+        m5 = LocalAggregator(**kw5).to(dev)
+        m5.validate = False
+        for k in ("means", "opa", "sem", "cov"):
+            t5[k].requires_grad_(True)
+        G5, N5 = t5["means"].shape[1], t5["pts"].shape[1]
+        up = torch.randn(B5, N5, 18, device=dev)              # resident upstream gradient (dL/dlogits)
+        wrt = [t5["means"], t5["opa"], t5["sem"], t5["cov"]]
+
+        def fwd_bwd(i):
+            logits = m5(t5["pts"], t5["means"], t5["opa"], t5["sem"], t5["scales"], t5["cov"])
+            torch.autograd.grad(logits, wrt, up)
+            all_reduce_step()
+
+        def fwd_only(i):
+            with torch.no_grad():
+                m5(t5["pts"], t5["means"], t5["opa"], t5["sem"], t5["scales"], t5["cov"])
+        for i in range(3):
+            fwd_bwd(i)
+        ms = timed_region(20, fwd_bwd) / 20
+        ms_f = timed_region(20, fwd_only) / 20
+        algf, algb = _algorithmic_bytes(G5, N5), _algorithmic_bytes_bwd(G5, N5)
+        out["fwd_bwd"] = {"value": world * B5 * G_COUNTED / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                          "fwd_ms": ms_f, "bwd_ms": ms - ms_f, "samples_per_gpu": B5, "global_batch": B5 * world,
+                          "hbm_frac_fwd": B5 * algf / (ms_f * 1e-3) / 1e9 / peak,
+                          "hbm_frac_bwd": B5 * algb / (max(ms - ms_f, 1e-6) * 1e-3) / 1e9 / peak,
+                          "scaling": "weak", "collective": "one scalar all-reduce (NCCL) per step, asynchronous",
+                          "what": "BASELINE config 5 (gs25600 bs 32 over 8 GPUs = 4 samples per GPU): module forward + "
+                                  "autograd backward, each one batched C-ABI call; max over ranks"}
+        del t5, up, m5
+    except Exception as e:
+        out["fwd_bwd"] = {"error": repr(e)}
+
+    try:
+        # ---- config 4: probabilistic head, 2 samples per GPU ----
+        B4 = 2
+        kw4, t4 = batch_inputs("prob_gs6400", tuple(rank * 100 + 20 + b for b in range(B4)))
+        m4 = LocalAggregatorProb(**kw4).to(dev)
+        m4.validate = False
+        G4, N4 = t4["means"].shape[1], t4["pts"].shape[1]
+
+        def fwd4(i):
+            with torch.no_grad():
+                m4(t4["pts"], t4["means"], t4["opa"], t4["sem"], t4["scales"], t4["cov"])
+            all_reduce_step()
+        for i in range(3):
+            fwd4(i)
+        f_ms = timed_region(10, fwd4) / 10
+        for k in ("means", "opa", "sem", "cov"):
+            t4[k].requires_grad_(True)
+        wrt4 = [t4["means"], t4["opa"], t4["sem"], t4["cov"]]
+        ups = [torch.randn(B4, N4, 18, device=dev), torch.randn(B4, N4, device=dev), torch.randn(B4, N4, device=dev)]
+
+        def fb4(i):
+            lg, bl, de = m4(t4["pts"], t4["means"], t4["opa"], t4["sem"], t4["scales"], t4["cov"])
+            torch.autograd.grad([lg, bl, de], wrt4, ups)
+            all_reduce_step()
+        for i in range(2):
+            fb4(i)
+        fb_ms = timed_region(5, fb4) / 5
+        pairs = 1.298e8                                       # in-box pairs per sample of this config (oracle count, seed 0)
+        algf, algb = _algorithmic_bytes(G4, N4, prob=True), _algorithmic_bytes_bwd(G4, N4, prob=True)
+        b_ms = max(fb_ms - f_ms, 1e-6)
+        out["prob"] = {"value": world * B4 * G4 / (f_ms * 1e-3), "unit": UNIT, "fwd_ms": f_ms, "fwd_bwd_ms": fb_ms,
+                       "samples_per_gpu": B4, "global_batch": B4 * world,
+                       "roofs_fwd": {"hbm_frac": B4 * algf / (f_ms * 1e-3) / 1e9 / peak,
+                                     "fp32_tflops": B4 * pairs * 70 / (f_ms * 1e-3) / 1e12,
+                                     "fp32_frac": B4 * pairs * 70 / (f_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+                                     "binding": "fp32 (CUDA cores)"},
+                       "roofs_bwd": {"hbm_frac": B4 * algb / (b_ms * 1e-3) / 1e9 / peak,
+                                     "fp32_tflops": B4 * pairs * 150 / (b_ms * 1e-3) / 1e12,
+                                     "fp32_frac": B4 * pairs * 150 / (b_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+                                     "binding": "fp32 (CUDA cores) + L1 gather"},
+                       "fp32_peak_tflops": FP32_PEAK_TFLOPS, "pairs_per_sample": pairs,
+                       "what": "BASELINE config 4 (prob/nuscenes_gs6400, bs 4 over 2 GPUs = 2 samples per GPU): 1.3e8 (voxel, "
+                               "Gaussian) pairs per sample at ~70 flop (fwd) / ~150 flop (bwd) each make it compute-bound; "
+                               "both roofs reported"}
+        del t4, ups, m4
+    except Exception as e:
+        out["prob"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    return out if rank == 0 else {}
+
+
+def side_measurements(dev, kw, inp0, resident, desc):
+    """Reported next to the headline (not part of it): backward, DAF, and the reference CUDA ops on the same GPU
+    when oracle/_ref travelled with the repo."""
+    import torch
+    from gaussianformer_b200.splat import LocalAggregator
     from gaussianformer_b200.synthetic import make_daf_inputs, make_splat_inputs
     from gaussianformer_b200.ops import DeformableAggregationFunction as DAF
     out = {}
@@ -411,29 +642,18 @@ def side_measurements(dev, kw, inp0, resident, desc):
         g = torch.randn_like(logits)
         out["splat_bwd_ms"] = timeit(lambda: torch.autograd.grad(logits, [t["means"], t["opa"], t["sem"], t["cov"]], g,
                                                                  retain_graph=True), reps=10)
-        kwp, inpp, _ = make_splat_inputs("prob_gs6400", seed=0, perturb=True)
-        mp = LocalAggregatorProb(**kwp).to(dev)
-        mp.validate = False
-        tp = {k: v.to(dev) for k, v in inpp.items()}
-        out["prob_gs6400_fwd_ms"] = timeit(lambda: mp(tp["pts"], tp["means"], tp["opa"], tp["sem"], tp["scales"], tp["cov"]), reps=10)
-        for k in ("means", "opa", "sem", "cov"):
-            tp[k].requires_grad_(True)
-        lg, bl, de = mp(tp["pts"], tp["means"], tp["opa"], tp["sem"], tp["scales"], tp["cov"])
-        gp = [torch.randn_like(lg), torch.randn_like(bl), torch.randn_like(de)]
-        out["prob_gs6400_bwd_ms"] = timeit(lambda: torch.autograd.grad([lg, bl, de], [tp["means"], tp["opa"], tp["sem"], tp["cov"]],
-                                                                       gp, retain_graph=True), reps=5)
-        del lg, bl, de, gp, tp
-        # BASELINE.json configs[2]: 144 000 Gaussians into the same grid (forward, voxel-centre points)
+        del logits, g, t
+        # BASELINE.json configs[2]: mIoU parity on the 144 000-Gaussian sample (the timing is `roofline_cfg3`)
         kwl, inpl, _ = make_splat_inputs("gs144000", seed=0, perturb=False)
         ml = LocalAggregator(**kwl).to(dev)
         ml.validate = False
         tl = {k: v.to(dev) for k, v in inpl.items()}
-        out["gs144000_fwd_ms"] = timeit(lambda: ml(tl["pts"], tl["means"], tl["opa"], tl["sem"], tl["scales"], tl["cov"]), reps=10)
         try:
             # north star: mIoU unchanged (SURVEY.md 8d recipe on the 144 000-Gaussian sample, whose arg-max spreads over
             # all 18 classes): fused arg-max of the CUDA path vs the CPU port's arg-max, scored with the reference's MeanIoU
             from gaussianformer_b200.metric import miou_parity, synthetic_labels
             _lg, occ = ml.forward_with_occupancy(tl["pts"], tl["means"], tl["opa"], tl["sem"], tl["scales"], tl["cov"])
+            _all_host_threads()
             _cpu_port_once(kwl, inpl)
             want = _LAST_PORT["logits"]
             labels, mask = synthetic_labels(want, want.shape[1])
@@ -441,7 +661,9 @@ def side_measurements(dev, kw, inp0, resident, desc):
             out["miou_parity_gs144000"] = {
                 "miou_cuda": r["new"][0], "miou_cpu_port": r["ref"][0], "abs_diff": r["abs_diff"],
                 "argmax_differences": int((occ.cpu().numpy().astype("int64") != want.argmax(1)).sum()),
-                "voxels": int(want.shape[0])}
+                "voxels": int(want.shape[0]),
+                "what": "fused arg-max vs the fp32 CPU port; the op-vs-op figure against the reference CUDA op is 0 "
+                        "differences (tests/test_parity_full_gpu.py, profiles/r02_parity/)"}
         except Exception as e:
             out["miou_parity_error"] = repr(e)
         del tl

@@ -54,6 +54,12 @@ def num_threads() -> int:
     return int(lib().gfo_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the following oracle calls (torchrun exports OMP_NUM_THREADS=1).  Returns what is in effect."""
+    lib().gfo_set_num_threads(int(n))
+    return num_threads()
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

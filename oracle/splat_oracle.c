@@ -97,6 +97,12 @@ int64_t gfo_build_voxel_lists(int G, int H, int W, int D, const int *means_int,
 
 void gfo_free(void *p) { free(p); }
 
+/* OpenMP threads of the following calls made by this thread (bench.py: all host cores, whatever OMP_NUM_THREADS a
+ * launcher such as torchrun exported) */
+void gfo_set_num_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+}
+
 int gfo_num_threads(void) {
 #if defined(_OPENMP)
     return omp_get_max_threads();

@@ -46,9 +46,11 @@ def test_daf_forward_backward_vs_oracle(embed, groups, levels):
     ref = oracle.daf_forward(f_np, s_np, st_np, loc.numpy(), w.numpy(), "f64")
     h.assert_close(out.detach().cpu().numpy(), ref, what="daf out")
     rf, rl, rw = oracle.daf_backward(f_np, s_np, st_np, loc.numpy(), w.numpy(), g.numpy(), "f64")
-    h.assert_close(gf.cpu().numpy(), rf, rtol=1e-3, atol=h.grad_tolerance(rf), what="grad feat")
-    h.assert_close(gw.cpu().numpy(), rw, rtol=1e-3, atol=h.grad_tolerance(rw), what="grad weights")
-    h.assert_close(gl.cpu().numpy(), rl, rtol=1e-3, atol=h.grad_tolerance(rl), what="grad loc")
+    rf32, rl32, rw32 = oracle.daf_backward(f_np, s_np, st_np, loc.numpy(), w.numpy(), g.numpy(), "f32")
+    # BASELINE gate, else K x the measured fp32 floor of the oracle's own arithmetic (helpers.assert_grad_parity)
+    h.assert_grad_parity(gf.cpu().numpy(), rf, rf32, what="grad feat")
+    h.assert_grad_parity(gw.cpu().numpy(), rw, rw32, what="grad weights")
+    h.assert_grad_parity(gl.cpu().numpy(), rl, rl32, what="grad loc")
 
 
 def test_daf_matches_reference_golden():
@@ -61,8 +63,15 @@ def test_daf_matches_reference_golden():
                                   levels=levels, visible_p=0.5, seed=4)
     _, _, _, out, (g, gf, gl, gw) = _run(fms, loc, w, backward_seed=int(gold["grad_seed"]))
     h.assert_close(out.detach().cpu().numpy(), gold["out"], what="daf out vs reference op")
-    for name, mine, ref in (("feat", gf, gold["grad_feat"]), ("loc", gl, gold["grad_loc"]), ("w", gw, gold["grad_weights"])):
-        h.assert_close(mine.cpu().numpy(), ref, rtol=1e-3, atol=h.grad_tolerance(ref), what="grad %s vs reference op" % name)
+    # both are fp32 atomically-accumulated sums: the slack is the golden's own measured distance from the fp64 oracle
+    feat_t, shape_t, start_t = DAF.feature_maps_format(fms)
+    r64 = oracle.daf_backward(feat_t.contiguous().numpy(), shape_t.numpy(), start_t.numpy(), loc.numpy(), w.numpy(), g.numpy(), "f64")
+    for name, mine, ref, truth in (("feat", gf, gold["grad_feat"], r64[0]), ("loc", gl, gold["grad_loc"], r64[1]),
+                                   ("w", gw, gold["grad_weights"], r64[2])):
+        floor = float(np.abs(ref.astype(np.float64) - truth).max())
+        err = np.abs(mine.cpu().numpy().astype(np.float64) - ref)
+        tol = np.maximum(h.ATOL + h.RTOL * np.abs(ref), (h.K_FLOOR + 1.0) * floor)
+        assert (err <= tol).all(), f"grad {name} vs reference op: max err {err.max():.3e}, reference floor {floor:.3e}"
 
 
 def test_daf_full_size_properties():
@@ -146,9 +155,10 @@ def test_daf_fused_forward_backward_vs_oracle(embed, groups, levels, masks):
     g = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
     out.backward(g.cuda())
     rf, rl, rw = oracle.daf_fused_backward(f_np, s_np, st_np, loc.numpy(), logits.numpy(), g.numpy(), pm_np, wm_np, "f64")
-    h.assert_close(feat.grad.cpu().numpy(), rf, rtol=1e-3, atol=h.grad_tolerance(rf), what="fused grad feat")
-    h.assert_close(lg_d.grad.cpu().numpy(), rw, rtol=1e-3, atol=h.grad_tolerance(rw), what="fused grad logits")
-    h.assert_close(loc_d.grad.cpu().numpy(), rl, rtol=1e-3, atol=h.grad_tolerance(rl), what="fused grad loc")
+    rf32, rl32, rw32 = oracle.daf_fused_backward(f_np, s_np, st_np, loc.numpy(), logits.numpy(), g.numpy(), pm_np, wm_np, "f32")
+    h.assert_grad_parity(feat.grad.cpu().numpy(), rf, rf32, what="fused grad feat")
+    h.assert_grad_parity(lg_d.grad.cpu().numpy(), rw, rw32, what="fused grad logits")
+    h.assert_grad_parity(loc_d.grad.cpu().numpy(), rl, rl32, what="fused grad loc")
     if pm is not None:
         assert torch.all(out[0, 0] == 0) and torch.all(lg_d.grad[0, 0] == 0)
 

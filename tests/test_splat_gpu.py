@@ -58,11 +58,7 @@ def test_base_backward_vs_oracle():
     _, t, out = _run(kw, inp, variant, requires_grad=True)
     g = torch.randn(out.shape, generator=torch.Generator().manual_seed(7))
     out.backward(g.cuda())
-    gm, go, gs, gc = h.oracle_backward(kw, inp, variant, (g.numpy(),))
-    import oracle
-    for name, mine, ref in (("means", t["means"].grad[0], gm), ("opa", t["opa"].grad[0], go),
-                            ("sem", t["sem"].grad[0], gs), ("cov", t["cov"].grad[0], oracle.cov6_grad_to_3x3(gc))):
-        h.assert_close(mine.cpu().numpy(), ref, rtol=1e-3, atol=h.grad_tolerance(ref), what="grad " + name)
+    h.check_module_grads(t, kw, inp, variant, (g.numpy(),), what="base")
 
 
 @pytest.mark.parametrize("per_axis", [False, True])
@@ -77,11 +73,7 @@ def test_prob_backward_vs_oracle(per_axis):
     ref_f = h.oracle_forward(kw, inp, variant, "f32")
     saved = dict(logits=lg.detach().cpu().numpy(), bin_logits=bl.detach().cpu().numpy(),
                  probability=ref_f["probability"])
-    gm, go, gs, gc = h.oracle_backward(kw, inp, variant, tuple(x.numpy() for x in g), saved)
-    import oracle
-    for name, mine, ref in (("means", t["means"].grad[0], gm), ("opa", t["opa"].grad[0], go),
-                            ("sem", t["sem"].grad[0], gs), ("cov", t["cov"].grad[0], oracle.cov6_grad_to_3x3(gc))):
-        h.assert_close(mine.cpu().numpy(), ref, rtol=2e-3, atol=5 * h.grad_tolerance(ref), what="grad " + name)
+    h.check_module_grads(t, kw, inp, variant, tuple(x.numpy() for x in g), what="prob", saved_from=saved)
 
 
 def test_generic_points_path():
@@ -164,11 +156,7 @@ def test_backward_generic_points_and_unaligned_gradients():
         g_dev.copy_(g)
         assert g_dev.data_ptr() % 16 == 4 * offset
         out.backward(g_dev)
-        gm, go, gs, gc = h.oracle_backward(kw, inp2, variant, (g.numpy(),))
-        for name, mine, ref in (("means", t["means"].grad[0], gm), ("opa", t["opa"].grad[0], go),
-                                ("sem", t["sem"].grad[0], gs), ("cov", t["cov"].grad[0], oracle.cov6_grad_to_3x3(gc))):
-            h.assert_close(mine.cpu().numpy(), ref, rtol=1e-3, atol=h.grad_tolerance(ref),
-                           what=f"grad {name} (N={len(idx)}, offset={offset})")
+        h.check_module_grads(t, kw, inp2, variant, (g.numpy(),), what=f"(N={len(idx)}, offset={offset})")
 
 
 def test_reference_asserts_are_raised():
@@ -224,7 +212,8 @@ def test_vs_reference_goldens(fixture, cfg, seed, perturb, per_axis):
     gen = torch.Generator().manual_seed(int(gold["grad_seed"]))
     if variant == "base":
         h.assert_close(out.detach().cpu().numpy(), gold["logits"], what="logits vs reference op")
-        out.backward(torch.randn(out.shape, generator=gen).cuda())
+        g_base = torch.randn(out.shape, generator=gen)
+        out.backward(g_base.cuda())
     else:
         lg, bl, de = out
         z = gold["probability"]
@@ -235,10 +224,14 @@ def test_vs_reference_goldens(fixture, cfg, seed, perturb, per_axis):
         g = [torch.randn(lg.shape, generator=gen), torch.randn(bl.shape, generator=gen), torch.randn(de.shape, generator=gen)]
         torch.autograd.backward([lg, bl, de], [x.cuda() for x in g])
     import oracle
-    for name, mine, ref in (("means", t["means"].grad[0], gold["means_grad"]), ("opa", t["opa"].grad[0], gold["opacity_grad"]),
-                            ("sem", t["sem"].grad[0], gold["semantics_grad"]),
-                            ("cov", t["cov"].grad[0], oracle.cov6_grad_to_3x3(gold["cov_grad"]))):
-        h.assert_close(mine.cpu().numpy(), ref, rtol=2e-3, atol=5 * h.grad_tolerance(ref), what="grad %s vs reference op" % name)
+    golden = {"means": gold["means_grad"], "opa": gold["opacity_grad"], "sem": gold["semantics_grad"],
+              "cov": oracle.cov6_grad_to_3x3(gold["cov_grad"])}
+    if variant == "base":
+        grads_np, saved = (g_base.numpy(),), None
+    else:   # the reference's backward received the reference's own forward outputs
+        grads_np = tuple(x.numpy() for x in g)
+        saved = dict(logits=gold["logits"], bin_logits=gold["bin_logits"], probability=gold["probability"])
+    h.check_module_grads(t, kw, inp, variant, grads_np, what=fixture, saved_from=saved, golden=golden)
 
 
 def test_fused_argmax_matches_logits():
@@ -287,9 +280,7 @@ def test_other_class_counts(C, variant):
         torch.autograd.backward(list(out), [x.cuda() for x in g])
         saved = dict(logits=out[0].detach().cpu().numpy(), bin_logits=out[1].detach().cpu().numpy(),
                      probability=h.oracle_forward(kw, inp, variant, "f32")["probability"])
-    gm, go, gs, gc = h.oracle_backward(kw, inp, variant, tuple(x.numpy() for x in g), saved)
-    h.assert_close(t["sem"].grad[0].cpu().numpy(), gs, rtol=2e-3, atol=5 * h.grad_tolerance(gs), what=f"C={C} grad sem")
-    h.assert_close(t["means"].grad[0].cpu().numpy(), gm, rtol=2e-3, atol=5 * h.grad_tolerance(gm), what=f"C={C} grad means")
+    h.check_module_grads(t, kw, inp, variant, tuple(x.numpy() for x in g), what=f"C={C}", saved_from=saved)
 
 
 def test_forward_from_scales_and_rotations():
@@ -322,25 +313,34 @@ def test_miou_is_unchanged():
     of the fp64 oracle with 10 % of the voxels re-drawn (seed 1), mask = label != 0; the fused arg-max of the CUDA
     path and the oracle's arg-max are scored with the reference's MeanIoU (misc/metric_util.py:35-111).  The
     gs144000-style sample (N(0,1) class vectors, no empty Gaussian) is used because its arg-max spreads over all 18
-    classes (on gs25600_solid the empty Gaussian's 10*e_17 wins every voxel and the score degenerates).  Only
-    voxels whose top two classes tie numerically may differ (assert_argmax_parity); for scale, the oracle's own
-    fp32 build differs from its fp64 build on 234 of the 640 000 voxels = 0.033 mIoU points on this sample."""
+    classes (on gs25600_solid the empty Gaussian's 10*e_17 wins every voxel and the score degenerates).
+    Gates: no arg-max difference on a numerically decided voxel; MeanIoU equal within 1e-4 points over the
+    decided voxels; over ALL voxels (numerical ties included) within 1e-4 + K x the measured distance between the
+    oracle's own fp32 and fp64 builds (the fp32 floor of the arithmetic on this sample, printed).
+    The full-size op-vs-op version of this test is tests/test_parity_full_gpu.py (0 differences against the reference
+    op on configs 2, 3 and 4, profiles/r02_parity/)."""
     from gaussianformer_b200.metric import miou_parity, synthetic_labels
     kw, inp, variant = h.splat_case("gs144000", 5, False, dict(G=20000))
     m = h.make_module(kw, variant)
     t = h.to_dev(inp)
     logits, occ = m.forward_with_occupancy(t["pts"], t["means"], t["opa"], t["sem"], t["scales"], t["cov"])
     ref = h.oracle_forward(kw, inp, variant)["logits"]
+    ref32 = h.oracle_forward(kw, inp, variant, "f32")["logits"]
     h.assert_argmax_parity(logits.cpu().numpy(), ref)
     C = ref.shape[1]
     labels, mask = synthetic_labels(ref, C)
-    r = miou_parity(occ.cpu(), ref.argmax(1), labels, mask, C)
-    flips = int((occ.cpu().numpy().astype(np.int64) != ref.argmax(1)).sum())
-    # (half of this grid's voxels see only far tails, |logit| < 1e-5, where the top two classes are within rounding
-    # of each other; the bounds are ~8x the fp32-vs-fp64 oracle figures quoted above)
-    assert flips <= 3e-3 * ref.shape[0], f"{flips} arg-max differences on {ref.shape[0]} voxels"
-    assert r["abs_diff"] <= 0.3, r
-    assert r["ref"][0] > 50.0            # the labels are a meaningful target (10 % noise), not a degenerate score
+    tie = torch.as_tensor(h.tie_voxels(ref))
+    am, am64, am32 = occ.cpu().long(), torch.as_tensor(ref.argmax(1)), torch.as_tensor(ref32.argmax(1))
+    assert int(((am != am64) & ~tie).sum()) == 0
+    r_dec = miou_parity(am, am64, labels, mask & ~tie, C)
+    r_all = miou_parity(am, am64, labels, mask, C)
+    floor = miou_parity(am32, am64, labels, mask, C)
+    print("mIoU all voxels", r_all, "fp32-vs-fp64 oracle floor", floor["abs_diff"], "flips", int((am != am64).sum()),
+          "oracle fp32 flips", int((am32 != am64).sum()), "tie voxels", int(tie.sum()))
+    assert r_dec["abs_diff"] <= 1e-4, r_dec
+    assert r_all["abs_diff"] <= 1e-4 + h.K_FLOOR * floor["abs_diff"], (r_all, floor)
+    assert int((am != am64).sum()) <= max(64, h.K_FLOOR * int((am32 != am64).sum()))
+    assert r_all["ref"][0] > 50.0            # the labels are a meaningful target (10 % noise), not a degenerate score
 
 
 def test_forward_on_grid_is_forward_on_the_voxel_centres():

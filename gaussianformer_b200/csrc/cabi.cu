@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 // defined in the kernel translation units
 int plan_forward_workspace(const gf_splat_desc &d, void *base, SplatWorkspace *ws);
 int launch_prep(const gf_splat_desc &d, const gf_splat_inputs &in, const SplatWorkspace &ws, uint32_t initial_flags,
-                cudaStream_t stream);
+                cudaStream_t stream, bool raw_records = false);
 int launch_render(const gf_splat_desc &d, const gf_splat_inputs &in, const gf_splat_outputs &out,
                   const SplatWorkspace &ws, bool tile_path, int num_sms, cudaStream_t stream);
 size_t backward_workspace_bytes(const gf_splat_desc &d);

@@ -79,8 +79,8 @@ constexpr int kPackThreads = 64;   // small CTAs: ~400 of them cover the 148 SMs
 // running (programmatic stream serialization).  The kernel must call pdl_wait() before it touches
 // anything the preceding kernel writes.  GF_B200_PDL=0 falls back to plain stream order.
 bool pdl_enabled();
-template <class Params>
-cudaError_t launch_chained(void (*kernel)(Params), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Params &p) {
+template <class... Params>
+cudaError_t launch_chained(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Params &...p) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -91,7 +91,7 @@ cudaError_t launch_chained(void (*kernel)(Params), dim3 grid, dim3 block, size_t
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, p);
+    return cudaLaunchKernelEx(&cfg, kernel, p...);
 }
 
 

@@ -25,6 +25,7 @@ struct PackParams {
     uint32_t *masks;
     uint32_t *pack_flags;
     int rec;     // floats per record
+    int raw;     // != 0: records for the bin-centric backward -- (mu, opacity | c6 as given | sem as given), nothing folded
     int st;      // supertile edge
     int nsx, nsy;
     int nwords;
@@ -73,7 +74,9 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
         boxes[g] = bx;
 
         const float a_ = c6[0], b_ = c6[1], c_ = c6[2], d_ = c6[3], e_ = c6[4], f_ = c6[5];
-        if (p.d.variant == GF_SPLAT_PROB) {
+        if (p.raw) {
+            // backward: the kernel needs the opacity, the inverse covariance and the class vector themselves
+        } else if (p.d.variant == GF_SPLAT_PROB) {
             // (2*pi)^-1.5 * sqrt(det) * opacity   (localagg_prob/src/forward.cu:77-78)
             const float det = a_ * b_ * c_ + 2.f * d_ * e_ * f_ - a_ * e_ * e_ - b_ * f_ * f_ - c_ * d_ * d_;
             amp = kKappa * sqrtf(det) * amp;
@@ -85,8 +88,13 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
         }
         float4 *rec = reinterpret_cast<float4 *>(records + static_cast<size_t>(g) * p.rec);
         rec[0] = make_float4(mu[0], mu[1], mu[2], amp);
-        rec[1] = make_float4(-0.5f * kLog2e * a_, -0.5f * kLog2e * b_, -0.5f * kLog2e * c_, -kLog2e * d_);
-        rec[2] = make_float4(-kLog2e * e_, -kLog2e * f_, 0.f, 0.f);
+        if (p.raw) {
+            rec[1] = make_float4(a_, b_, c_, d_);
+            rec[2] = make_float4(e_, f_, 0.f, 0.f);
+        } else {
+            rec[1] = make_float4(-0.5f * kLog2e * a_, -0.5f * kLog2e * b_, -0.5f * kLog2e * c_, -kLog2e * d_);
+            rec[2] = make_float4(-kLog2e * e_, -kLog2e * f_, 0.f, 0.f);
+        }
 #pragma unroll
         for (int q = 0; q < 5; ++q)
             if (q < nq) rec[3 + q] = make_float4(semv[4 * q], semv[4 * q + 1], semv[4 * q + 2], semv[4 * q + 3]);
@@ -260,8 +268,9 @@ int plan_forward_workspace(const gf_splat_desc &d, void *base, SplatWorkspace *w
 }
 
 int launch_prep(const gf_splat_desc &d, const gf_splat_inputs &in, const SplatWorkspace &ws,
-                uint32_t initial_flags, cudaStream_t stream) {
+                uint32_t initial_flags, cudaStream_t stream, bool raw_records) {
     PackParams pp;
+    pp.raw = raw_records ? 1 : 0;
     pp.d = d;
     pp.in = in;
     pp.records = ws.records;

@@ -23,6 +23,10 @@ namespace gf {
 __global__ void __launch_bounds__(256) voxel_map_kernel(const BwdParams pb) {
     pdl_launch_dependents();   // the pair kernels may become resident; they wait before using the map
     const BwdParams p = sample_bwd(pb, blockIdx.y);
+    if (p.bin_active) {   // launched behind the bin-centric kernel, which verified the point order: canonical -> done
+        pdl_wait();
+        if (*p.canon != 0) return;
+    }
     const int H = p.d.H, W = p.d.W, D = p.d.D;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *p.big_ctr = 0ull;
@@ -100,47 +104,58 @@ __device__ __forceinline__ void walk_pairs(const BwdParams &p, GaussAcc<C, PROB>
         walk_pairs_t<C, PROB, false>(p, acc, box, canon);
 }
 
-template <int C, bool PROB>
+template <int C, bool PROB, bool STRIDED>
 __global__ void __launch_bounds__(bwd_threads(PROB), bwd_ctas(PROB)) backward_small_kernel(const BwdParams pb) {
     constexpr int kBwdThreads = bwd_threads(PROB);
     const BwdParams p = sample_bwd(pb, blockIdx.y);
     const int lane = threadIdx.x & 31;
-    // no early exit for the warps past G: they redo the last Gaussian and skip the stores, which keeps
-    // every warp provably converged at the shuffles below
     if (p.bin_active) {   // canonical points: the bin-centric kernel has produced the gradients; nothing to do here
         pdl_wait();
         if (*p.canon != 0) return;
     }
-    const int g_raw = blockIdx.x * (kBwdThreads / 32) + (threadIdx.x >> 5);
-    const bool live = g_raw < p.d.G;
-    const int g = live ? g_raw : p.d.G - 1;
-    GaussAcc<C, PROB> acc;
-    acc.load(p, g);
-    int lo[3], hi[3];
-    uint32_t err = 0;
-    const bool empty = gaussian_box(p.d, p.in, g, acc.mu, lo, hi, err) || !live;
-    BoxWalk box;
-    box.init(lo, hi, empty, p.d.W, p.d.D);
-    const bool big = box.vol > kBigBox;
-    pdl_launch_dependents();
-    pdl_wait();   // everything above read the caller's inputs only; the map, the canonical flag and the queue follow
-    const bool canon = *p.canon != 0;   // then voxel index == point index and the map need not be read
-    if (canon && p.bin_active) return;  // canonical points: the bin-centric kernel has produced the gradients
-    if (!big) {
-        box.start(lane, box.vol, 32);
-        walk_pairs<C, PROB>(p, acc, box, canon);
-    } else {
-        if (lane == 0) {
-            const unsigned long long nch = static_cast<unsigned long long>((box.vol + p.chunk - 1) / p.chunk);
-            const unsigned long long old = atomicAdd(p.big_ctr, (1ull << 40) | nch);
-            p.big[old >> 40] = make_uint2(static_cast<uint32_t>(g), static_cast<uint32_t>(old & ((1ull << 40) - 1)));
+    // One Gaussian per warp and pass; the grid normally covers all Gaussians in one pass.  Behind the bin-centric kernel
+    // this kernel is only its (rare) fallback and is launched with a small grid that strides over the Gaussians
+    // (STRIDED; a separate instantiation, so that the one-pass kernel keeps its register allocation).
+    const int per_cta = kBwdThreads / 32;
+    const int passes = STRIDED ? (p.d.G + gridDim.x * per_cta - 1) / (gridDim.x * per_cta) : 1;
+    bool waited = false;
+#pragma unroll 1
+    for (int pass = 0; pass < passes; ++pass) {
+        // no early exit for the warps past G: they redo the last Gaussian and skip the stores, which keeps
+        // every warp provably converged at the shuffles below
+        const int g_raw = (pass * gridDim.x + blockIdx.x) * per_cta + (threadIdx.x >> 5);
+        const bool live = g_raw < p.d.G;
+        const int g = live ? g_raw : p.d.G - 1;
+        GaussAcc<C, PROB> acc;
+        acc.load(p, g);
+        int lo[3], hi[3];
+        uint32_t err = 0;
+        const bool empty = gaussian_box(p.d, p.in, g, acc.mu, lo, hi, err) || !live;
+        BoxWalk box;
+        box.init(lo, hi, empty, p.d.W, p.d.D);
+        const bool big = box.vol > kBigBox;
+        if (!waited) {
+            pdl_launch_dependents();
+            pdl_wait();   // everything above read the caller's inputs only; the map, the canonical flag and the queue follow
+            waited = true;
         }
+        const bool canon = *p.canon != 0;   // then voxel index == point index and the map need not be read
+        if (!big) {
+            box.start(lane, box.vol, 32);
+            walk_pairs<C, PROB>(p, acc, box, canon);
+        } else {
+            if (lane == 0) {
+                const unsigned long long nch = static_cast<unsigned long long>((box.vol + p.chunk - 1) / p.chunk);
+                const unsigned long long old = atomicAdd(p.big_ctr, (1ull << 40) | nch);
+                p.big[old >> 40] = make_uint2(static_cast<uint32_t>(g), static_cast<uint32_t>(old & ((1ull << 40) - 1)));
+            }
+        }
+        // small boxes: final values; queued boxes: zeros (the big kernel accumulates atomically)
+        float x[32];
+        acc.to_vector(x);
+        const float v = warp_transpose_reduce(x, lane);
+        finish<C, PROB>(p, g, v, live ? lane : 32, false);
     }
-    // small boxes: final values; queued boxes: zeros (the big kernel accumulates atomically)
-    float x[32];
-    acc.to_vector(x);
-    const float v = warp_transpose_reduce(x, lane);
-    finish<C, PROB>(p, g, v, live ? lane : 32, false);
 }
 
 template <int C, bool PROB>
@@ -309,35 +324,48 @@ static int launch_backward_t(const BwdParams &bp, const BwdWorkspace &ws, bool s
     GF_REQUIRE(B <= 65535, GF_ERR_UNSUPPORTED, "splat backward: batch above 65535");
     // canon words (non-zero = "still canonical") and the voxel->point maps (-1 = empty) in one fill
     GF_CUDA_TRY(cudaMemsetAsync(bp.canon, 0xFF, ws.cv_bytes, stream));
-    if (bp.bin_active) GF_CUDA_TRY(cudaMemsetAsync(ws.sums, 0, ws.sums_bytes, stream));   // accumulated with atomics
     const long long want = (static_cast<long long>(d.N) + 255) / 256;
     const int grid0 = static_cast<int>(want < 16ll * num_sms ? (want > 0 ? want : 1) : 16ll * num_sms);
-    voxel_map_kernel<<<dim3(grid0, B), 256, 0, stream>>>(bp);   // plain stream order: never overlaps the previous call
-    GF_CUDA_TRY(cudaGetLastError());
-    if (PROB) {
+    auto launch_aux = [&](bool chained) -> int {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid0, B); cfg.blockDim = dim3(256); cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = (chained && pdl_enabled()) ? 1 : 0;
         GF_CUDA_TRY(cudaLaunchKernelEx(&cfg, prob_aux_kernel, bp, static_cast<int>(C)));
-    }
+        return GF_OK;
+    };
     if (bp.bin_active) {
-        // supertile lists for this call (pack is launched in plain stream order: it starts when everything above has
-        // completed; list and the bin kernel are chained to it), then the bin-centric kernel
+        // Canonical points (checked by the bin kernel itself): memset -> [prob_aux] -> pack -> list -> bin -> finish, and
+        // the Gaussian-centric chain below finds the flag set and returns.  pack is launched in plain stream order (it
+        // starts when everything above has completed); the kernels after it are chained to their predecessor.
+        GF_CUDA_TRY(cudaMemsetAsync(ws.sums, 0, ws.sums_bytes, stream));   // accumulated with atomics
+        if (PROB) { int rc = launch_aux(false); if (rc != GF_OK) return rc; }
         SplatWorkspace fws;
         plan_forward_workspace(d, ws.fwd, &fws);
         int rc = launch_prep(d, bp.in, fws, 0u, stream, true);
         if (rc != GF_OK) return rc;
         rc = launch_backward_bin(bp, fws, ws.sums, stream);
         if (rc != GF_OK) return rc;
+        // the Gaussian-centric chain is only the fallback now: small grids (they return at once when the points are canonical)
+        GF_CUDA_TRY(launch_chained(voxel_map_kernel, dim3(num_sms, B), dim3(256), 0, stream, bp));
+    } else {
+        voxel_map_kernel<<<dim3(grid0, B), 256, 0, stream>>>(bp);   // plain stream order: never overlaps the previous call
+        GF_CUDA_TRY(cudaGetLastError());
+        if (PROB) { int rc = launch_aux(true); if (rc != GF_OK) return rc; }
     }
     constexpr int kBwdThreads = bwd_threads(PROB);
     const int per_cta = kBwdThreads / 32;
-    GF_CUDA_TRY(launch_chained(backward_small_kernel<C, PROB>, dim3((d.G + per_cta - 1) / per_cta, B), dim3(kBwdThreads), 0, stream, bp));
+    int small_ctas = (d.G + per_cta - 1) / per_cta;
     int big_ctas = (num_sms * bwd_ctas(PROB) * 2 + B - 1) / B;   // per sample: together they fill the GPU twice over
     if (big_ctas < 32) big_ctas = 32;
+    if (bp.bin_active) {
+        if (small_ctas > num_sms) small_ctas = num_sms;
+        big_ctas = num_sms;
+    }
+    if (bp.bin_active) GF_CUDA_TRY(launch_chained(backward_small_kernel<C, PROB, true>, dim3(small_ctas, B), dim3(kBwdThreads), 0, stream, bp));
+    else GF_CUDA_TRY(launch_chained(backward_small_kernel<C, PROB, false>, dim3(small_ctas, B), dim3(kBwdThreads), 0, stream, bp));
     GF_CUDA_TRY(launch_chained(backward_big_kernel<C, PROB>, dim3(big_ctas, B), dim3(kBwdThreads), 0, stream, bp));
     if (srt) GF_CUDA_TRY(launch_chained(srt_grad_kernel, dim3((d.G + 127) / 128, B), dim3(128), 0, stream, bp));
     return GF_OK;

@@ -47,7 +47,7 @@ struct alignas(64) BinMaps {
 
 struct BinParams {
     const float *records;     // raw records of the pack kernel: [B*G, 32]
-    float *sums;              // [B*G, 32] raw sums, zero-filled by the host
+    float *sums;              // [B, 32, G] raw sums (value-major), zero-filled by the host
     const PackedBox *boxes;
     const int32_t *lists;
     const int32_t *counts;
@@ -118,8 +118,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) backward_bin_kernel(const BwdP
     }
     pdl_launch_dependents();
     __syncthreads();
-    pdl_wait();   // boxes / lists of the preparation kernels, and (transitively) the canonical flag and the aux terms
-    if (*p.canon == 0) return;   // points are not in canonical voxel order: the Gaussian-centric kernels take over
+    pdl_wait();   // boxes / lists of the preparation kernels, and (transitively) the aux terms of the prob variant
 
     if (tid == 0) {
         constexpr uint32_t kBytes = 512u * C * 4u + 512u * 3u * 4u + (PROB ? 512u * 16u : 0u);
@@ -230,6 +229,27 @@ __global__ void __launch_bounds__(kBinThreads, 2) backward_bin_kernel(const BwdP
         if (!tiles_ready) {   // the tiles were in flight during the first Phase A
             mbar_wait(&sm.bar, 0);
             tiles_ready = true;
+            // canonical-order check of MY bin's points (point n must lie in voxel n): this kernel assumed it; a
+            // violation clears the flag, bin_finish_kernel then discards the sums and the Gaussian-centric kernels
+            // (which build the voxel -> point map) produce the gradients instead
+#pragma unroll
+            for (int r = 0; r < 512 / NT; ++r) {
+                const int i = tid + r * NT, col = i >> 4, z = i & 15;
+                const int X = binX0 + (col >> 2), Y = binY0 + (col & 3), Z = binZ0 + z;
+                if (X < H && Y < W && Z < D) {
+                    int vx, vy, vz;
+                    if (p.in.points_int) {
+                        const long long n = (static_cast<long long>(X) * W + Y) * D + Z;
+                        vx = p.in.points_int[3 * n]; vy = p.in.points_int[3 * n + 1]; vz = p.in.points_int[3 * n + 2];
+                    } else {
+                        const float *pp = &sm.pts[col * (kBinZ * 3) + z * 3];
+                        vx = voxel_coord(pp[0], p.d.pc_min[0], p.d.grid_size);
+                        vy = voxel_coord(pp[1], p.d.pc_min[1], p.d.grid_size);
+                        vz = voxel_coord(pp[2], p.d.pc_min[2], p.d.grid_size);
+                    }
+                    if (vx != X || vy != Y || vz != Z) *p.canon = 0;   // benign race: every writer stores 0
+                }
+            }
         }
         __syncthreads();
 
@@ -307,23 +327,55 @@ __global__ void __launch_bounds__(kBinThreads, 2) backward_bin_kernel(const BwdP
                 const int v0 = ((sub & 4) ? 16 : 0) + ((sub & 2) ? 8 : 0) + ((sub & 1) ? 4 : 0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (v0 + i < GaussAcc<C, PROB>::kVals) atomicAdd(sums + static_cast<size_t>(g) * 32 + v0 + i, x[i]);
+                    if (v0 + i < GaussAcc<C, PROB>::kVals) atomicAdd(sums + static_cast<size_t>(v0 + i) * p.d.G + g, x[i]);
             }
         }
     }
 }
 
-// One warp per Gaussian: the raw sums of all bins -> the gradients (the per-Gaussian linear maps of finish()).
+// One thread per Gaussian: the raw sums of all bins ([32][G], value-major: coalesced reads) -> the gradients, i.e. the
+// per-Gaussian linear maps of finish() (splat_bwd_common.cuh): d(mean) = -A * sum(w d), d(cov) = -(1/2 | 1) * sum(w d d^T)
+// (+ the determinant terms of the prob variant), d(sem) = opacity * sum(E g) for the base variant.
 template <int C, bool PROB>
-__global__ void __launch_bounds__(256) bin_finish_kernel(const BwdParams pb, const float *sums_all) {
+__global__ void __launch_bounds__(128) bin_finish_kernel(const BwdParams pb, const float *sums_all) {
+    pdl_launch_dependents();
     pdl_wait();
     const BwdParams p = sample_bwd(pb, blockIdx.y);
     if (*p.canon == 0) return;
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (g >= p.d.G) return;
-    const float *sums = sums_all + (static_cast<size_t>(blockIdx.y) * p.d.G + g) * 32;
-    finish<C, PROB>(p, g, sums[lane], lane, false);
+    const int g = blockIdx.x * 128 + threadIdx.x;
+    const int G = p.d.G;
+    if (g >= G) return;
+    const float *sums = sums_all + static_cast<size_t>(blockIdx.y) * 32 * G + g;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < GaussAcc<C, PROB>::kVals; ++i) v[i] = __ldg(sums + static_cast<size_t>(i) * G);
+    float c6[6];
+    load_cov6_in(p.d, p.in, g, c6);
+    const float a = c6[0], b = c6[1], c = c6[2], d = c6[3], e = c6[4], f = c6[5];
+    p.gr.means_grad[3 * g + 0] = -(a * v[0] + d * v[1] + f * v[2]);
+    p.gr.means_grad[3 * g + 1] = -(d * v[0] + b * v[1] + e * v[2]);
+    p.gr.means_grad[3 * g + 2] = -(f * v[0] + e * v[1] + c * v[2]);
+    p.gr.opacity_grad[g] = v[3];
+    float gc[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) gc[i] = (i < 3) ? -0.5f * v[4 + i] : -v[4 + i];
+    if (PROB) {
+        const float sg = v[10 + C];
+        const float m[6] = {b * c - e * e, a * c - f * f, a * b - d * d, 2.f * (e * f - c * d), 2.f * (d * f - a * e), 2.f * (d * e - b * f)};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) gc[i] = fmaf(sg, m[i], gc[i]);
+    }
+    if (p.d.cov_stride == 9) {   // the six gathered entries [0,4,8,1,5,2] of the 3x3 carry the gradient, the lower triangle gets 0
+        float *o = p.gr.cov_grad + 9 * static_cast<size_t>(g);
+        o[0] = gc[0]; o[1] = gc[3]; o[2] = gc[5]; o[3] = 0.f; o[4] = gc[1]; o[5] = gc[4]; o[6] = 0.f; o[7] = 0.f; o[8] = gc[2];
+    } else {
+        float *o = p.gr.cov_grad + 6 * static_cast<size_t>(g);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) o[i] = gc[i];
+    }
+    const float scale = PROB ? 1.f : p.in.opacities[g];
+#pragma unroll
+    for (int k = 0; k < C; ++k) p.gr.semantics_grad[static_cast<size_t>(g) * C + k] = scale * v[10 + k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -394,7 +446,7 @@ static int launch_bin_t(const BwdParams &bp, const BinParams &np, const BinMaps 
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     GF_CUDA_TRY(cudaLaunchKernelEx(&cfg, backward_bin_kernel<C, PROB>, bp, np, maps));
     const float *sums = np.sums;
-    GF_CUDA_TRY(launch_chained(bin_finish_kernel<C, PROB>, dim3((d.G + 7) / 8, B), dim3(256), 0, stream, bp, sums));
+    GF_CUDA_TRY(launch_chained(bin_finish_kernel<C, PROB>, dim3((d.G + 127) / 128, B), dim3(128), 0, stream, bp, sums));
     return GF_OK;
 }
 

@@ -153,6 +153,52 @@ def make_daf_inputs(num_anchor=25600, num_pts=9, batch=1, num_cams=6, embed_dims
     return feature_maps, loc, w.contiguous()
 
 
+def make_daf_inputs_projected(num_anchor=25600, num_pts=9, batch=1, num_cams=6, embed_dims=128, num_groups=4,
+                              levels=DAF_LEVELS_1600x864, seed=0, image_wh=(1600.0, 864.0), kp_sigma=0.3):
+    """A CORRELATED sampling workload: what ``DeformableFeatureAggregation`` really feeds the op.  Anchors are 3-D
+    points in the nuScenes volume; each anchor has ``num_pts`` key points scattered ``kp_sigma`` metres around it
+    (``SparseGaussian3DKeyPointsGenerator``: fixed + learnable offsets scaled by the Gaussian, deformable_module.py:17-90);
+    the key points are projected into ``num_cams`` pinhole cameras that look outward at 360/num_cams degree steps and
+    normalised by the image size (``project_points``, deformable_module.py:287-305).  A camera sees a key point when it
+    lies in front of it and inside the image; the other cameras get a location outside (0, 1) like the reference's.
+    Key points of one anchor therefore land a few pixels apart (and on the same rows of the coarse levels), unlike
+    ``make_daf_inputs`` whose locations are independent uniform draws.  Returns (feature_maps, loc, weights)."""
+    gen = torch.Generator().manual_seed(seed)
+    feature_maps = [torch.randn(batch, num_cams, embed_dims, h, w, generator=gen) for h, w in levels]
+    W_img, H_img = image_wh
+    P = num_anchor * num_pts
+    L = len(levels)
+    anchors = torch.rand(batch, num_anchor, 3, generator=gen) * torch.tensor([100.0, 100.0, 8.0]) + torch.tensor([-50.0, -50.0, -5.0])
+    kps = anchors[:, :, None, :] + torch.randn(batch, num_anchor, num_pts, 3, generator=gen) * kp_sigma
+    kps = kps.reshape(batch, P, 3)
+    focal = 0.8 * W_img
+    locs, vis = [], []
+    for m in range(num_cams):
+        yaw = 2 * math.pi * m / num_cams
+        fwd = torch.tensor([math.cos(yaw), math.sin(yaw), 0.0])
+        right = torch.tensor([math.sin(yaw), -math.cos(yaw), 0.0])
+        up = torch.tensor([0.0, 0.0, 1.0])
+        rel = kps - torch.tensor([0.0, 0.0, -3.2])                 # camera 1.8 m above the ground plane of the volume
+        depth = (rel * fwd).sum(-1)
+        u = focal * (rel * right).sum(-1) / depth.clamp(min=1e-5) + 0.5 * W_img
+        v = -focal * (rel * up).sum(-1) / depth.clamp(min=1e-5) + 0.5 * H_img
+        xy = torch.stack([u / W_img, v / H_img], -1)
+        ok = (depth > 1e-5) & (xy > 0).all(-1) & (xy < 1).all(-1)
+        xy = torch.where(ok[..., None], xy, torch.full_like(xy, 2.0))
+        locs.append(xy)
+        vis.append(ok)
+    loc = torch.stack(locs, 2).contiguous()                          # [B, P, M, 2]
+    inside = torch.stack(vis, 2)                                     # [B, P, M]
+    raw = torch.randn(batch, num_anchor, num_pts, num_cams, L, num_groups, generator=gen)
+    mask = inside.reshape(batch, num_anchor, num_pts, num_cams)[..., None, None].expand_as(raw)
+    all_miss = mask.sum(dim=[2, 3, 4], keepdim=True) == 0
+    raw = raw.masked_fill(~mask, -math.inf)
+    raw = torch.where(all_miss.expand_as(raw), torch.zeros_like(raw), raw)
+    w = raw.flatten(2, 4).softmax(dim=-2).reshape(batch, P, num_cams, L, num_groups)
+    w = w * (1 - all_miss.expand(-1, -1, num_pts, -1, -1, -1).reshape(batch, P, 1, 1, num_groups).float())
+    return feature_maps, loc, w.contiguous()
+
+
 def make_daf_fused_inputs(num_anchor=25600, num_pts=9, batch=1, num_cams=6, embed_dims=128, num_groups=4,
                           levels=DAF_LEVELS_1600x864, visible_p=0.22, seed=0, attn_drop=0.0):
     """Inputs of the fused caller path (``ops.deformable_aggregation_fused``): the same pyramid and sampling

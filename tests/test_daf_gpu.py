@@ -196,3 +196,30 @@ def test_daf_fused_full_size_equals_the_unfused_route():
     h.assert_close(outs[0], outs[1], what="fused vs unfused out")
     for name, a, b in zip(("feat", "loc", "logits"), grads[0], grads[1]):
         h.assert_close(a, b, rtol=1e-3, atol=h.grad_tolerance(b), what="fused vs unfused grad " + name)
+
+
+def test_tma_corner_box_variant_is_bit_identical():
+    """The TMA experiment (gf_debug_daf_forward_tma, include/gf_b200_debug.h): one cp.async.bulk.tensor box {C,2,2,1} per
+    visible (camera, level) pair with hardware zero fill for corners outside the map -- the same products in the same
+    order as the product kernel, so the outputs are equal bit for bit (incl. locations on and beyond the map border)."""
+    import ctypes
+    from gaussianformer_b200 import _lib
+    from gaussianformer_b200.ops.deformable_aggregation import _desc
+    levels = ((12, 20), (6, 10), (3, 5))
+    fms, loc, w = make_daf_inputs(num_anchor=80, num_pts=5, batch=2, num_cams=3, embed_dims=128, num_groups=4,
+                                  levels=levels, visible_p=0.6, seed=7)
+    loc[0, 0, 0] = torch.tensor([0.004, 0.996]); loc[0, 1, 1] = torch.tensor([0.999, 0.001]); loc[1, 2, 2] = torch.tensor([0.5, 0.0])
+    feat, shape, start = DAF.feature_maps_format([f.cuda() for f in fms])
+    feat = feat.contiguous()
+    loc_d, w_d = loc.cuda(), w.cuda()
+    ref = DAF.apply(feat, shape, start, loc_d, w_d)
+    d = _desc(feat, shape, loc_d, w_d)
+    hs = (ctypes.c_int32 * (2 * len(levels)))(*[v for hw in levels for v in hw])
+    hst = (ctypes.c_int32 * len(levels))(*[int(v) for v in start.cpu().tolist()])
+    out = torch.empty_like(ref)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(_lib.lib().gf_debug_daf_forward_tma(ctypes.byref(d), ctypes.c_void_p(feat.data_ptr()), hs, hst,
+                                                  ctypes.c_void_p(loc_d.data_ptr()), ctypes.c_void_p(w_d.data_ptr()),
+                                                  ctypes.c_void_p(out.data_ptr()), stream))
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)

@@ -147,18 +147,16 @@ __global__ void __launch_bounds__(256) gather_probe_kernel(const float *table, c
         const int mine = __ldg(idx + j);
 #pragma unroll 1
         for (int k0 = 0; k0 < 32; k0 += 8) {
-            float4 v[8];
+            const float *row[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float *row = table + static_cast<long long>(__shfl_sync(0xffffffffu, mine, k0 + k)) * row_floats;
-                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int c0 = lane * 4; c0 < row_floats; c0 += 128) {
-                    const float4 t = __ldg(reinterpret_cast<const float4 *>(row + c0));
-                    v[k].x += t.x; v[k].y += t.y; v[k].z += t.z; v[k].w += t.w;
-                }
+            for (int k = 0; k < 8; ++k) row[k] = table + static_cast<long long>(__shfl_sync(0xffffffffu, mine, k0 + k)) * row_floats;
+            for (int c0 = lane * 4; c0 < row_floats; c0 += 128) {
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float4 *>(row[k] + c0));   // eight loads in flight
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
             }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
         }
     }
     if (acc.x + acc.y + acc.z + acc.w == 123456.789f) sink[0] = acc.x;   // keeps the loads alive

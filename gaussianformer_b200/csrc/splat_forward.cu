@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
     RenderSmem<C> &sm = *reinterpret_cast<RenderSmem<C> *>(smem_raw);
 #ifdef GF_RENDER_TIMING
     const long long t_start = clock64();
-    if (threadIdx.x < 4) sm.t_phase[threadIdx.x] = 0ull;
+    if (threadIdx.x < 8) sm.t_phase[threadIdx.x] = 0ull;
 #endif
     const int sample = blockIdx.z / pb.nbx;
     const RenderParams pin = sample_params(pb, sample);   // inputs + workspace of my sample; outputs: see the epilogue
@@ -146,13 +146,21 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
             float A = t1 * dx;
             A = fmaf(g1.y * dy, dy, A);
             const float B = fmaf(g2.x, dy, g2.y * dx);
+            // the per-voxel part on packed fp32 pairs: voxels (0,1) and (2,3) share each instruction
 #pragma unroll
-            for (int v = 0; v < VOX; ++v) {
-                const float dz = g0.z - pz[v];
-                const float q = fmaf(fmaf(g1.z, dz, B), dz, A);
-                const float E = ((zb >> v) & 1u) ? ex2_approx(q) : 0.f;
-                wv[v] = PROB ? g0.w * E : E;      // base: the opacity is folded into the class vector (pack kernel)
-                if (PROB) { zsum[v] += wv[v]; dens[v] += E; keep[v] *= (1.f - E); }
+            for (int h2 = 0; h2 < VOX / 2; ++h2) {
+                const int v0 = 2 * h2, v1 = v0 + 1;
+                const float2 dz = __fadd2_rn(make_float2(g0.z, g0.z), make_float2(-pz[v0], -pz[v1]));
+                float2 q = __ffma2_rn(make_float2(g1.z, g1.z), dz, make_float2(B, B));
+                q = __ffma2_rn(q, dz, make_float2(A, A));
+                const float E0 = ((zb >> v0) & 1u) ? ex2_approx(q.x) : 0.f;
+                const float E1 = ((zb >> v1) & 1u) ? ex2_approx(q.y) : 0.f;
+                wv[v0] = PROB ? g0.w * E0 : E0;      // base: the opacity is folded into the class vector (pack kernel)
+                wv[v1] = PROB ? g0.w * E1 : E1;
+                if (PROB) {
+                    zsum[v0] += wv[v0]; dens[v0] += E0; keep[v0] *= (1.f - E0);
+                    zsum[v1] += wv[v1]; dens[v1] += E1; keep[v1] *= (1.f - E1);
+                }
             }
         } else {
             // general points: quadratic form on packed fp32 pairs, voxels (0,1) and (2,3) share each instruction
@@ -323,6 +331,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
         atomicAdd(t + 1, sm.t_phase[1]);
         atomicAdd(t + 2, sm.t_phase[2]);
         atomicAdd(t + 3, static_cast<unsigned long long>(clock64() - t_epi));
+        for (int i = 4; i < 8; ++i) atomicAdd(t + i, sm.t_phase[i]);   // bytes 48..79 (the status block is 256 bytes)
     }
 #endif
 }

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kListThreads) list_kernel(const ListParams p) 
         if (lane == 0 && e) atomicOr(&s_e, e);
         __syncthreads();
         if (threadIdx.x == 0) p.flags[0] = s_e;
-        else if (threadIdx.x < 16) p.flags[threadIdx.x] = 0u;   // words 4..11: cycle counters of a GF_RENDER_TIMING build
+        else if (threadIdx.x < 32) p.flags[threadIdx.x] = 0u;   // words 4..19: cycle counters of a GF_RENDER_TIMING build
     }
 }
 
@@ -256,7 +256,7 @@ int plan_forward_workspace(const gf_splat_desc &d, void *base, SplatWorkspace *w
         off = align_up(off + bytes, 256);
         return p;
     };
-    ws->flags = reinterpret_cast<uint32_t *>(take(64));
+    ws->flags = reinterpret_cast<uint32_t *>(take(256));
     ws->pack_flags = reinterpret_cast<uint32_t *>(take(B * size_t(ws->pack_ctas) * 4));
     ws->records = reinterpret_cast<float *>(take(B * size_t(d.G) * rec_floats(d.C) * 4));
     ws->boxes = reinterpret_cast<PackedBox *>(take(B * size_t(d.G) * sizeof(PackedBox)));

@@ -35,7 +35,7 @@ struct RenderSmem {
     int warp_count[2][NT / 32];
     float ce[NT / 32][2];                      // per-warp cross-entropy partials of the epilogue
 #ifdef GF_RENDER_TIMING
-    unsigned long long t_phase[4];             // CTA cycle sums: prologue, Phase A, Phase B, epilogue
+    unsigned long long t_phase[8];             // cycle sums: prologue, Phase A, Phase B, epilogue (thread 0); all warps: wait-full, wait-empty + issue, hit masks, walk
 #endif
 };
 
@@ -182,6 +182,9 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
         for (int k = 0; k < kRing - 1 && k < nchunks; ++k) issue(k, gb + k);
 #pragma unroll 1
         for (int k = 0; k < nchunks; ++k, ++gb) {
+#ifdef GF_RENDER_TIMING
+            const long long tk0 = clock64();
+#endif
             const int slot = gb % kRing;
             const uint32_t stage_base = smem_u32(&sm.stage[slot][0]);
             // bit j of `hits`: record j of this batch covers my column and my z quad (padded entries are all-zero)
@@ -201,7 +204,13 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
                 hits = (sx == 0 ? bx[0] : sx == 1 ? bx[1] : sx == 2 ? bx[2] : bx[3]) &
                        (sy == 0 ? by[0] : sy == 1 ? by[1] : sy == 2 ? by[2] : by[3]) & ((lane & 1) ? bz[1] : bz[0]);
             }
+#ifdef GF_RENDER_TIMING
+            const long long tw0 = clock64();
+#endif
             mbar_wait(&sm.bar_full[slot], (gb / kRing) & 1);
+#ifdef GF_RENDER_TIMING
+            const long long tw1 = clock64();
+#endif
             while (__any_sync(0xffffffffu, hits != 0)) {
                 const bool act = hits != 0;
                 const int j = act ? __ffs(static_cast<int>(hits)) - 1 : 0;   // my lowest remaining hit
@@ -212,8 +221,19 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
                 step(rv, (e >> my_zshift) & VMASK, act);
             }
             __syncwarp();
+#ifdef GF_RENDER_TIMING
+            const long long tw2 = clock64();
+#endif
             if (lane == 0) mbar_arrive_one(&sm.bar_empty[slot]);       // my warp is done with this slot
             if (k + kRing - 1 < nchunks) issue(k + kRing - 1, gb + kRing - 1);
+#ifdef GF_RENDER_TIMING
+            if (lane == 0) {
+                atomicAdd(&sm.t_phase[4], static_cast<unsigned long long>(tw1 - tw0));
+                atomicAdd(&sm.t_phase[5], static_cast<unsigned long long>(clock64() - tw2));
+                atomicAdd(&sm.t_phase[6], static_cast<unsigned long long>(tw0 - tk0));
+                atomicAdd(&sm.t_phase[7], static_cast<unsigned long long>(tw2 - tw1));
+            }
+#endif
         }
 #ifdef GF_RENDER_TIMING
         if (tid == 0) sm.t_phase[2] += static_cast<unsigned long long>(clock64() - tB0);

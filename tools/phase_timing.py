@@ -21,7 +21,8 @@ desc = _make_desc(G, N, 18, kw["H"], kw["W"], kw["D"], _lib.GF_SPLAT_PROB if var
 for rep in range(3):
     _, ws = splat_forward_raw(desc, t["pts"], t["means"], t["opa"], t["sem"], t["cov"].reshape(B, G, 9), scales=t["scales"])
 torch.cuda.synchronize()
-c = ws[16:48].view(torch.int64).cpu().tolist()
+c8 = ws[16:80].view(torch.int64).cpu().tolist()
+c = c8[:4]
 nct = ((kw["H"] + 7) // 8) * ((kw["W"] + 3) // 4) * ((kw["D"] + 15) // 16) * B
 names = ("prologue", "phase A", "phase B", "epilogue")
 tot = sum(c)
@@ -29,3 +30,8 @@ print(f"{cfg} batch {B}: {nct} CTAs; cycles per CTA (thread 0):")
 for n, v in zip(names, c):
     print(f"  {n:9s} {v / nct:9.0f}  ({100.0 * v / max(tot, 1):5.1f} %)")
 print(f"  total     {tot / nct:9.0f}")
+names2 = ("wait records (full)", "arrive + wait empty + issue next", "hit masks (ballots)", "walk (steps)")
+tot2 = sum(c8[4:])
+print("Phase B of ALL warps, cycles per warp:")
+for n, v in zip(names2, c8[4:]):
+    print(f"  {n:34s} {v / (4 * nct):9.0f}  ({100.0 * v / max(tot2, 1):5.1f} %)")

@@ -275,42 +275,57 @@ __global__ void __launch_bounds__(kBinThreads, 2) backward_bin_kernel(const BwdP
             const int vol = nx * ny * nz;   // 0 for a lane group without an entry
             GaussAcc<C, PROB> acc;
             acc.load_record(reinterpret_cast<const float4 *>(records + static_cast<size_t>(g) * 32));
-            // my lanes stride over the clipped box, z fastest; the stride is decomposed once into box steps
+            // My lanes stride over the clipped box, z fastest; the stride is decomposed once into box steps.  A whole-warp
+            // entry walks the two z halves of the box one after the other: the halves of the gradient tile are two TMA
+            // boxes whose distance is a multiple of 128 bytes, so lanes on the same column and z & 7 of different halves
+            // would hit the same banks (ncu: 39 % of the shared wavefronts of the prob config were such replays), while
+            // neighbouring columns of ONE half sit 16 banks apart.
             const int first = wide ? lane : sub, stride = wide ? 32 : 8;
-            int t = small_div(first, nz);
-            int iz = first - t * nz, ix = small_div(t, ny), iy = t - ix * ny;
-            const int t2 = small_div(stride, nz), sz = stride - t2 * nz, sx = small_div(t2, ny), sy = t2 - sx * ny;
+            const int nseg = wide ? 2 : 1;
 #pragma unroll 1
-            for (int idx = first; idx < vol; idx += stride) {
-                const int col = (x0 + ix) * kBinY + (y0 + iy), Z = z0 + iz;
-                PairData<C, PROB> pd;
-                pd.ok = true;
-                pd.shift = false;
-                const float *pp = &sm.pts[col * (kBinZ * 3) + Z * 3];
-                pd.px = pp[0]; pd.py = pp[1]; pd.pz = pp[2];
-                const float *row = &sm.grad[(Z >> 3) * (256 * C) + (col * 8 + (Z & 7)) * C];
-                if constexpr ((C & 1) == 0) {   // rows start 8-byte aligned
-#pragma unroll
-                    for (int k = 0; k < CP2; ++k) {
-                        const float2 v = *reinterpret_cast<const float2 *>(row + 2 * k);
-                        if (k & 1) { pd.raw[k >> 1].z = v.x; pd.raw[k >> 1].w = v.y; } else { pd.raw[k >> 1].x = v.x; pd.raw[k >> 1].y = v.y; }
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < CP2; ++k) {
-                        const float a = row[2 * k], b = (2 * k + 1 < C) ? row[2 * k + 1] : 0.f;
-                        if (k & 1) { pd.raw[k >> 1].z = a; pd.raw[k >> 1].w = b; } else { pd.raw[k >> 1].x = a; pd.raw[k >> 1].y = b; }
-                    }
+            for (int sg = 0; sg < nseg; ++sg) {
+                int zs = z0, nzh = nz;
+                if (wide) {
+                    zs = sg == 0 ? z0 : max(z0, 8);
+                    nzh = sg == 0 ? min(z0 + nz, 8) - z0 : z0 + nz - zs;
+                    if (nzh <= 0) continue;
                 }
-                if (PROB) pd.ax = sm.aux[col * kBinZ + Z];
-                acc.template consume<false>(pd);
-                iz += sz;
-                const int cz = iz >= nz;
-                iz -= cz ? nz : 0;
-                iy += sy + cz;
-                const int cy = iy >= ny;
-                iy -= cy ? ny : 0;
-                ix += sx + cy;
+                const int volh = nx * ny * nzh;
+                int t = small_div(first, nzh);
+                int iz = first - t * nzh, ix = small_div(t, ny), iy = t - ix * ny;
+                const int t2 = small_div(stride, nzh), sz = stride - t2 * nzh, sx = small_div(t2, ny), sy = t2 - sx * ny;
+#pragma unroll 1
+                for (int idx = first; idx < volh; idx += stride) {
+                    const int col = (x0 + ix) * kBinY + (y0 + iy), Z = zs + iz;
+                    PairData<C, PROB> pd;
+                    pd.ok = true;
+                    pd.shift = false;
+                    const float *pp = &sm.pts[col * (kBinZ * 3) + Z * 3];
+                    pd.px = pp[0]; pd.py = pp[1]; pd.pz = pp[2];
+                    const float *row = &sm.grad[(Z >> 3) * (256 * C) + (col * 8 + (Z & 7)) * C];
+                    if constexpr ((C & 1) == 0) {   // rows start 8-byte aligned
+#pragma unroll
+                        for (int k = 0; k < CP2; ++k) {
+                            const float2 v = *reinterpret_cast<const float2 *>(row + 2 * k);
+                            if (k & 1) { pd.raw[k >> 1].z = v.x; pd.raw[k >> 1].w = v.y; } else { pd.raw[k >> 1].x = v.x; pd.raw[k >> 1].y = v.y; }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CP2; ++k) {
+                            const float a = row[2 * k], b = (2 * k + 1 < C) ? row[2 * k + 1] : 0.f;
+                            if (k & 1) { pd.raw[k >> 1].z = a; pd.raw[k >> 1].w = b; } else { pd.raw[k >> 1].x = a; pd.raw[k >> 1].y = b; }
+                        }
+                    }
+                    if (PROB) pd.ax = sm.aux[col * kBinZ + Z];
+                    acc.template consume<false>(pd);
+                    iz += sz;
+                    const int cz = iz >= nzh;
+                    iz -= cz ? nzh : 0;
+                    iy += sy + cz;
+                    const int cy = iy >= ny;
+                    iy -= cy ? ny : 0;
+                    ix += sx + cy;
+                }
             }
             __syncwarp();
             float x[32];

@@ -5,9 +5,11 @@ Run on a B200 box (the reference kernels are CUDA-only):
     gpurun -- 'python tests/golden/make_golden_ref.py gpurun_out/golden'
 
 then copy gpurun_out/golden/*.npz into tests/golden/.  Inputs are NOT stored: they are re-created
-bit-identically from (config name, seed) by gaussianformer_b200.synthetic on the CPU.  The host
-preparation below restates the reference's Python wrapper with torch ops on the GPU, as the
-reference does (model/head/localagg/local_aggregate/__init__.py:137-143).
+bit-identically from (config name, seed) by gaussianformer_b200.synthetic on the CPU.  oracle/ref_op.py
+restates the reference's Python host preparation with torch ops on the GPU, as the reference does
+(model/head/localagg/local_aggregate/__init__.py:137-143), around the unmodified native op.
+The mid-size fixture (2000 Gaussians + the whole-grid one on the full 200 x 200 x 16 grid) stores every 61st logits
+row, the fp64 column sums of all rows and the complete gradients (0.9 MB instead of 46 MB).
 """
 import os
 import sys
@@ -27,54 +29,35 @@ SPLAT_CASES = [  # (fixture, config, seed, overrides, module, per_axis, perturb)
     ("ref_splat_prob_tiny", "tiny_prob", 0, None, "gf_ref_localagg_prob", False, False),
     ("ref_splat_probfast_tiny", "tiny_prob", 2, None, "gf_ref_localagg_prob_fast", True, True),
 ]
+# mid-size: 2000 Gaussians + the whole-grid "empty" one on the FULL 200 x 200 x 16 grid (config 2's grid)
+MID_CASE = ("ref_splat_base_mid", "gs25600_solid", 7, dict(G=2000), "gf_ref_localagg", False, False)
 
 
-def ref_host_prep(pts, means, scales, pc_min, grid, mult, radii_min, per_axis):
-    points_int = ((pts - pc_min) / grid).to(torch.int)
-    means_int = ((means - pc_min) / grid).to(torch.int)
-    if per_axis:
-        radii = torch.ceil(scales * mult / grid).to(torch.int)
-    else:
-        radii = torch.ceil(scales.max(dim=-1)[0] * mult / grid).to(torch.int)
-    if radii_min is not None:
-        radii = radii.clamp(min=radii_min)
-    return points_int.contiguous(), means_int.contiguous(), radii.contiguous()
+MID_STRIDE = 61   # the mid-size golden keeps every 61st logits row (the full 640000 x 18 tensor would be 46 MB)
 
 
-def run_splat(name, cfg, seed, overrides, modname, per_axis, perturb, outdir):
+def run_splat(name, cfg, seed, overrides, modname, per_axis, perturb, outdir, row_stride=1):
+    """One sample through the UNMODIFIED reference op (oracle/ref_op.py restates its Python host preparation)."""
+    from oracle import ref_op
     kw, inp, variant = make_splat_inputs(cfg, seed=seed, perturb=perturb, overrides=overrides)
-    mod = build_ref.load_ref(modname)
-    dev = torch.device("cuda")
-    t = {k: v[0].to(dev) for k, v in inp.items()}
-    pc_min = torch.tensor(kw["pc_min"], dtype=torch.float, device=dev)[None]
-    prob = variant == "prob"
-    pi, mi, radii = ref_host_prep(t["pts"], t["means"], t["scales"], pc_min, kw["grid_size"],
-                                  kw["scale_multiplier"], 1 if prob else None, per_axis)
-    cov6 = t["cov"].flatten(1)[:, [0, 4, 8, 1, 5, 2]].contiguous()
-    H, W, D = kw["H"], kw["W"], kw["D"]
+    if per_axis:
+        variant = "prob_fast"
     gen = torch.Generator().manual_seed(1000 + seed)
-    N = t["pts"].shape[0]
-    save = {}
-    if not prob:
-        R, logits, geom, binning, img = mod.local_aggregate(t["pts"], pi, t["means"], mi, t["opa"], t["sem"], radii,
-                                                            cov6, H, W, D)
-        g = torch.randn(N, 18, generator=gen).to(dev)
-        gm, go, gs, gc = mod.local_aggregate_backward(geom, binning, img, H, W, D, R, t["means"], t["pts"], pi, cov6,
-                                                      t["opa"], t["sem"], g)
-        save.update(logits=logits, num_pairs=np.int64(R))
-    else:
-        R, logits, binl, dens, probability, geom, binning, img = mod.local_aggregate(
-            t["pts"], pi, t["means"], mi, t["opa"], t["sem"], radii, cov6, H, W, D)
-        g = torch.randn(N, 18, generator=gen).to(dev)
-        gb = torch.randn(N, generator=gen).to(dev)
-        gd = torch.randn(N, generator=gen).to(dev)
-        gm, go, gs, gc = mod.local_aggregate_backward(geom, binning, img, H, W, D, R, t["means"], t["pts"], pi, cov6,
-                                                      t["opa"], t["sem"], logits, binl, dens, probability, g, gb, gd)
-        save.update(logits=logits, bin_logits=binl, density=dens, probability=probability, num_pairs=np.int64(R))
-    save.update(means_grad=gm, opacity_grad=go, semantics_grad=gs, cov_grad=gc)
-    torch.cuda.synchronize()
-    arrays = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for k, v in save.items()}
+    N = inp["pts"].shape[1]
+    grads = (torch.randn(N, 18, generator=gen),)
+    if variant != "base":
+        grads = grads + (torch.randn(N, generator=gen), torch.randn(N, generator=gen))
+    r = ref_op.splat(kw, inp, variant, grads)
+    save = {k: v for k, v in r.items() if k != "num_pairs"}
+    arrays = {k: v.detach().cpu().numpy() for k, v in save.items()}
+    arrays["num_pairs"] = np.int64(r["num_pairs"])
     arrays["grad_seed"] = np.int64(1000 + seed)
+    if row_stride > 1:   # mid-size fixture: a row sample of the logits + per-class column sums of ALL rows (fp64)
+        full = arrays.pop("logits")
+        arrays["logits_rows"] = full[::row_stride].copy()
+        arrays["row_stride"] = np.int64(row_stride)
+        arrays["logits_colsum"] = full.astype(np.float64).sum(0)
+        arrays["logits_abs_colsum"] = np.abs(full.astype(np.float64)).sum(0)
     np.savez_compressed(os.path.join(outdir, name + ".npz"), **arrays)
     print(name, {k: getattr(v, "shape", v) for k, v in arrays.items()})
 
@@ -103,4 +86,5 @@ if __name__ == "__main__":
     os.makedirs(outdir, exist_ok=True)
     for case in SPLAT_CASES:
         run_splat(*case, outdir)
+    run_splat(*MID_CASE, outdir, row_stride=MID_STRIDE)
     run_daf(outdir)

@@ -57,6 +57,30 @@ def test_splat_oracle_matches_reference_op(fixture, cfg, seed, perturb, per_axis
             h.assert_close(mine, ref, rtol=2e-3, atol=5 * h.grad_tolerance(ref), what=f"{precision} grad {name}")
 
 
+def test_splat_oracle_matches_reference_op_mid_size():
+    """2000 Gaussians + the whole-grid "empty" one on the full 200 x 200 x 16 grid (config 2's grid): identical pair
+    count, the sampled logits rows and the column sums of ALL rows, and the complete gradients of the reference op."""
+    path = os.path.join(GOLD, "ref_splat_base_mid.npz")
+    if not os.path.exists(path):
+        pytest.skip("mid-size golden not generated yet")
+    gold = np.load(path)
+    kw, inp, variant = h.splat_case("gs25600_solid", 7, False, dict(G=2000))
+    stride = int(gold["row_stride"])
+    fwd = h.oracle_forward(kw, inp, variant, "f64")
+    assert fwd["num_pairs"] == int(gold["num_pairs"])
+    h.assert_close(fwd["logits"][::stride], gold["logits_rows"], what="sampled logits rows")
+    # column sums over all 640 000 rows: the fp32 reference rows sum to the fp64 oracle's within their elementwise gate
+    tol = h.ATOL * fwd["logits"].shape[0] + h.RTOL * gold["logits_abs_colsum"]
+    assert np.all(np.abs(fwd["logits"].sum(0) - gold["logits_colsum"]) <= tol)
+    N = inp["pts"].shape[1]
+    g = torch.randn(N, 18, generator=torch.Generator().manual_seed(int(gold["grad_seed"]))).numpy()
+    g64, g32 = h.oracle_grads(kw, inp, variant, (g,))
+    ref = {"means": gold["means_grad"], "opa": gold["opacity_grad"], "sem": gold["semantics_grad"],
+           "cov": oracle.cov6_grad_to_3x3(gold["cov_grad"])}
+    for name in ref:   # the reference op is an fp32 evaluation: gate, else K x the fp32 oracle's own floor
+        h.assert_grad_parity(ref[name], g64[name], g32[name], what="reference-op golden grad " + name)
+
+
 def test_daf_oracle_matches_reference_op():
     gold = np.load(os.path.join(GOLD, "ref_daf_small.npz"))
     levels = ((12, 20), (6, 10), (3, 5))

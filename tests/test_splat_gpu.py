@@ -234,6 +234,27 @@ def test_vs_reference_goldens(fixture, cfg, seed, perturb, per_axis):
     h.check_module_grads(t, kw, inp, variant, grads_np, what=fixture, saved_from=saved, golden=golden)
 
 
+def test_vs_reference_golden_mid_size():
+    """The mid-size reference-op golden (full config-2 grid, 2000 Gaussians + the whole-grid one)."""
+    path = os.path.join(GOLD, "ref_splat_base_mid.npz")
+    if not os.path.exists(path):
+        pytest.skip("mid-size golden not generated yet")
+    gold = np.load(path)
+    kw, inp, variant = h.splat_case("gs25600_solid", 7, False, dict(G=2000))
+    _, t, out = _run(kw, inp, variant, requires_grad=True)
+    stride = int(gold["row_stride"])
+    got = out.detach().cpu().numpy()
+    h.assert_close(got[::stride], gold["logits_rows"], what="sampled logits rows vs reference op")
+    tol = h.ATOL * got.shape[0] + h.RTOL * gold["logits_abs_colsum"]
+    assert np.all(np.abs(got.astype(np.float64).sum(0) - gold["logits_colsum"]) <= tol)
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(int(gold["grad_seed"])))
+    out.backward(g.cuda())
+    import oracle
+    golden = {"means": gold["means_grad"], "opa": gold["opacity_grad"], "sem": gold["semantics_grad"],
+              "cov": oracle.cov6_grad_to_3x3(gold["cov_grad"])}
+    h.check_module_grads(t, kw, inp, variant, (g.numpy(),), what="mid golden", golden=golden)
+
+
 def test_fused_argmax_matches_logits():
     kw, inp, variant = h.splat_case("gs25600_solid", 2, True, dict(G=2000))
     m = h.make_module(kw, variant)

@@ -188,8 +188,13 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
                 }
             }
         }
+#ifdef GF_EXPERIMENT_STUB_ACC   // experiment: how fast is the walk without the class accumulation? (results are wrong)
+        constexpr int kAccChunks = 1;
+#else
+        constexpr int kAccChunks = (C + 3) / 4;
+#endif
 #pragma unroll
-        for (int c4 = 0; c4 < (C + 3) / 4; ++c4) {
+        for (int c4 = 0; c4 < kAccChunks; ++c4) {
             const float4 s4 = rec.chunk(3 + c4);
 #pragma unroll
             for (int v = 0; v < VOX; ++v) {

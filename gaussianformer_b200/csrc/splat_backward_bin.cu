@@ -444,11 +444,8 @@ static int launch_bin_t(const BwdParams &bp, const BinParams &np, const BinMaps 
     GF_REQUIRE(nby <= 65535 && static_cast<long long>(np.nbx) * B <= 65535, GF_ERR_UNSUPPORTED,
                "splat backward: grid x batch too large for the bin launch");
     const size_t smem = sizeof(BinSmem<C, PROB>);
-    static bool configured = false;
-    if (!configured) {
-        GF_CUDA_TRY(cudaFuncSetAttribute(backward_bin_kernel<C, PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
-    }
+    // per call: the attribute is per device, and a process may drive several
+    GF_CUDA_TRY(cudaFuncSetAttribute(backward_bin_kernel<C, PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nzc, nby, np.nbx * B);
     cfg.blockDim = dim3(kBinThreads);

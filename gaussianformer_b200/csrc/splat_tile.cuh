@@ -21,14 +21,16 @@ constexpr int kBatch = 32;      // records staged per ring slot; a lane keeps it
 #endif
 constexpr int kRing = GF_TILE_RING;   // ring slots: a warp may run up to kRing-2 batches ahead of the slowest one
 
-// Shared-memory row of a staged record.  The eight 16-byte chunks of a 128-byte record are stored XOR-swizzled by
-// the row (chunk c of row j sits at position c ^ (j & 7)), so that lanes of one warp reading the same chunk of
-// DIFFERENT records fall into different bank groups.
+// Shared-memory row of a staged record: the 128-byte record followed by 16 bytes of padding, so that chunk c of row j
+// starts at bank group (j + c) mod 8 and lanes of one warp reading the same chunk of DIFFERENT records fall into
+// different bank groups -- the effect of an XOR swizzle, but a chunk's address is row + 16*c, an immediate offset of the
+// load (the XOR cost one LOP3 per chunk and step: 8 of 92 instructions).
 template <int C>
 struct RenderSmem {
     static constexpr int REC = rec_floats(C);
+    static constexpr int ROW = REC + 4;        // floats per staged row
     static constexpr int NT = kRenderThreads;
-    alignas(128) float stage[kRing][kBatch * REC];
+    alignas(128) float stage[kRing][kBatch * ROW];
     alignas(8) uint2 list[kQuadSeg + kBatch];  // x: box relative to the bin as bit masks, y: Gaussian index
     alignas(8) uint64_t bar_full[kRing];       // records of the slot have landed (one cp.async arrival per thread)
     alignas(8) uint64_t bar_empty[kRing];      // every warp is done with the slot (one arrival per warp)
@@ -50,13 +52,12 @@ __device__ __forceinline__ void mbar_arrive_one(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// One staged record as a lane sees it: `addr` is the shared-space address of the row with the swizzle already folded
-// in (the row is 128-byte aligned, so the fold is an OR), chunk i is one XOR away.
+// One staged record as a lane sees it: `addr` is the shared-space address of its row, chunk i sits 16*i bytes further.
 struct RecView {
     uint32_t addr;
     __device__ __forceinline__ float4 chunk(int i) const {
         float4 v;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr ^ (static_cast<uint32_t>(i) << 4)));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + 16u * static_cast<uint32_t>(i)));
         return v;
     }
 };
@@ -75,13 +76,12 @@ struct RecView {
 template <int C, class Step>
 __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &sm, int binX0, int binY0, int binZ0,
                                           int my_zshift, Step &&step) {
-    constexpr int REC = rec_floats(C);
+    constexpr int REC = rec_floats(C), ROW = RenderSmem<C>::ROW;
     constexpr int NT = kRenderThreads, NWARP = NT / 32, VOX = kVoxT;
     constexpr uint32_t VMASK = (1u << VOX) - 1u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.d.H, W = p.d.W, D = p.d.D;
     if (tid == 0) {
-        if (smem_u32(&sm.stage[0][0]) & 127u) __trap();   // RecView folds the swizzle into the address with an OR
 #pragma unroll
         for (int r = 0; r < kRing; ++r) {
             mbar_init(&sm.bar_full[r], NT);
@@ -172,8 +172,7 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
                 const int piece = tid + NT * q, row = piece >> 3, col = (piece & 7) * 4;
                 if (piece < kBatch * 8 && k * kBatch + row < nlist) {
                     const uint32_t g = sm.list[k * kBatch + row].y;
-                    const int dcol = (((piece & 7) ^ (row & 7)) * 4);      // swizzled chunk position (see RecView)
-                    cp_async16(&sm.stage[slot][row * REC + dcol], p.records + static_cast<size_t>(g) * REC + col);
+                    cp_async16(&sm.stage[slot][row * ROW + col], p.records + static_cast<size_t>(g) * REC + col);
                 }
             }
             cp_async_arrive_on(&sm.bar_full[slot]);
@@ -211,13 +210,16 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
 #ifdef GF_RENDER_TIMING
             const long long tw1 = clock64();
 #endif
-            while (__any_sync(0xffffffffu, hits != 0)) {
+            // the warp takes as many steps as its busiest lane has hits in this batch
+            const int nsteps = __reduce_max_sync(0xffffffffu, __popc(hits));
+#pragma unroll 1
+            for (int st = 0; st < nsteps; ++st) {
                 const bool act = hits != 0;
                 const int j = act ? __ffs(static_cast<int>(hits)) - 1 : 0;   // my lowest remaining hit
                 hits &= hits - 1;                                             // 0 stays 0
                 const uint32_t e = sm.list[k * kBatch + j].x;
                 RecView rv;
-                rv.addr = stage_base + static_cast<uint32_t>(j) * (REC * 4) + ((static_cast<uint32_t>(j) & 7u) << 4);
+                rv.addr = stage_base + static_cast<uint32_t>(j) * (ROW * 4);
                 step(rv, (e >> my_zshift) & VMASK, act);
             }
             __syncwarp();

@@ -1,0 +1,9 @@
+set +e
+out=gpurun_out/r02_q; mkdir -p $out
+timeout 900 python -m pytest tests/test_splat_gpu.py tests/test_cabi_gpu.py tests/test_batch_fused_gpu.py tests/test_parity_full_gpu.py -m gpu -q -x 2>&1 | tail -2
+for rep in 1 2; do timeout 300 python bench.py --steps 200 --warmup 20 --no-extras > $out/bench_$rep.json 2> $out/bench_$rep.err; python - <<PY
+import json
+d = json.loads(open("$out/bench_$rep.json").read().strip().splitlines()[-1])
+print("default", $rep, "ms/step", round(d["ms_per_step"], 5), "render_ms", round(d["roofline"]["kernel_ms"], 5), "e2e_ms", round(d["e2e"]["ms_per_step"], 4))
+PY
+done

@@ -131,63 +131,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
 #endif
     // One step of a lane = one (record, my 4 voxels) evaluation: exponent and weights from the record's three geometry
     // chunks, then the class accumulation (4 x C/2 packed FMAs) with its class chunks read where they are used.
-    auto step = [&](const RecView rec, uint32_t zb, bool active) {
-        if (!active) return;
-        const float4 g0 = rec.chunk(0), g1 = rec.chunk(1), g2c = rec.chunk(2);
-        const float2 g2 = make_float2(g2c.x, g2c.y);
-        float wv[VOX];
-        if (column) {
-            // My 4 points share x and y (voxel centres of one z column -- every shipped config,
-            // dataset/transform_3d.py:484-499 without perturbation): the exponent is a quadratic
-            // in dz alone, q = (cc*dz + B)*dz + A, with A and B evaluated once per record.
-            const float dx = g0.x - px[0], dy = g0.y - py[0];
-            float t1 = g1.x * dx;
-            t1 = fmaf(g1.w, dy, t1);
-            float A = t1 * dx;
-            A = fmaf(g1.y * dy, dy, A);
-            const float B = fmaf(g2.x, dy, g2.y * dx);
-            // the per-voxel part on packed fp32 pairs: voxels (0,1) and (2,3) share each instruction
-#pragma unroll
-            for (int h2 = 0; h2 < VOX / 2; ++h2) {
-                const int v0 = 2 * h2, v1 = v0 + 1;
-                const float2 dz = __fadd2_rn(make_float2(g0.z, g0.z), make_float2(-pz[v0], -pz[v1]));
-                float2 q = __ffma2_rn(make_float2(g1.z, g1.z), dz, make_float2(B, B));
-                q = __ffma2_rn(q, dz, make_float2(A, A));
-                const float E0 = ((zb >> v0) & 1u) ? ex2_approx(q.x) : 0.f;
-                const float E1 = ((zb >> v1) & 1u) ? ex2_approx(q.y) : 0.f;
-                wv[v0] = PROB ? g0.w * E0 : E0;      // base: the opacity is folded into the class vector (pack kernel)
-                wv[v1] = PROB ? g0.w * E1 : E1;
-                if (PROB) {
-                    zsum[v0] += wv[v0]; dens[v0] += E0; keep[v0] *= (1.f - E0);
-                    zsum[v1] += wv[v1]; dens[v1] += E1; keep[v1] *= (1.f - E1);
-                }
-            }
-        } else {
-            // general points: quadratic form on packed fp32 pairs, voxels (0,1) and (2,3) share each instruction
-#pragma unroll
-            for (int h2 = 0; h2 < VOX / 2; ++h2) {
-                const int v0 = 2 * h2, v1 = v0 + 1;
-                const float2 dx = __fadd2_rn(make_float2(g0.x, g0.x), make_float2(-px[v0], -px[v1]));
-                const float2 dy = __fadd2_rn(make_float2(g0.y, g0.y), make_float2(-py[v0], -py[v1]));
-                const float2 dz = __fadd2_rn(make_float2(g0.z, g0.z), make_float2(-pz[v0], -pz[v1]));
-                float2 t1 = __fmul2_rn(make_float2(g1.x, g1.x), dx);
-                t1 = __ffma2_rn(make_float2(g1.w, g1.w), dy, t1);
-                t1 = __ffma2_rn(make_float2(g2.y, g2.y), dz, t1);
-                float2 t2 = __fmul2_rn(make_float2(g1.y, g1.y), dy);
-                t2 = __ffma2_rn(make_float2(g2.x, g2.x), dz, t2);
-                float2 q = __fmul2_rn(t1, dx);
-                q = __ffma2_rn(t2, dy, q);
-                q = __ffma2_rn(__fmul2_rn(make_float2(g1.z, g1.z), dz), dz, q);
-                const float E0 = ((zb >> v0) & 1u) ? ex2_approx(q.x) : 0.f;
-                const float E1 = ((zb >> v1) & 1u) ? ex2_approx(q.y) : 0.f;
-                wv[v0] = PROB ? g0.w * E0 : E0;
-                wv[v1] = PROB ? g0.w * E1 : E1;
-                if (PROB) {
-                    zsum[v0] += wv[v0]; dens[v0] += E0; keep[v0] *= (1.f - E0);
-                    zsum[v1] += wv[v1]; dens[v1] += E1; keep[v1] *= (1.f - E1);
-                }
-            }
-        }
+    auto accumulate = [&](const RecView rec, const float (&wv)[VOX]) {
 #ifdef GF_EXPERIMENT_STUB_ACC   // experiment: how fast is the walk without the class accumulation? (results are wrong)
         constexpr int kAccChunks = 1;
 #else
@@ -204,7 +148,71 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
             }
         }
     };
-    walk_tile<C>(pin, sm, binX0, binY0, binZ0, my_zshift, step);
+    // My 4 points share x and y (voxel centres of one z column -- every shipped config,
+    // dataset/transform_3d.py:484-499 without perturbation): the exponent is a quadratic
+    // in dz alone, q = (cc*dz + B)*dz + A, with A and B evaluated once per record; the per-voxel part runs on
+    // packed fp32 pairs (voxels (0,1) and (2,3) share each instruction).
+    auto step_column = [&](const RecView rec, uint32_t zb, bool active) {
+        if (!active) return;
+        const float4 g0 = rec.chunk(0), g1 = rec.chunk(1), g2c = rec.chunk(2);
+        float wv[VOX];
+        const float dx = g0.x - px[0], dy = g0.y - py[0];
+        float t1 = g1.x * dx;
+        t1 = fmaf(g1.w, dy, t1);
+        float A = t1 * dx;
+        A = fmaf(g1.y * dy, dy, A);
+        const float B = fmaf(g2c.x, dy, g2c.y * dx);
+#pragma unroll
+        for (int h2 = 0; h2 < VOX / 2; ++h2) {
+            const int v0 = 2 * h2, v1 = v0 + 1;
+            const float2 dz = __fadd2_rn(make_float2(g0.z, g0.z), make_float2(-pz[v0], -pz[v1]));
+            float2 q = __ffma2_rn(make_float2(g1.z, g1.z), dz, make_float2(B, B));
+            q = __ffma2_rn(q, dz, make_float2(A, A));
+            const float E0 = ((zb >> v0) & 1u) ? ex2_approx(q.x) : 0.f;
+            const float E1 = ((zb >> v1) & 1u) ? ex2_approx(q.y) : 0.f;
+            wv[v0] = PROB ? g0.w * E0 : E0;      // base: the opacity is folded into the class vector (pack kernel)
+            wv[v1] = PROB ? g0.w * E1 : E1;
+            if (PROB) {
+                zsum[v0] += wv[v0]; dens[v0] += E0; keep[v0] *= (1.f - E0);
+                zsum[v1] += wv[v1]; dens[v1] += E1; keep[v1] *= (1.f - E1);
+            }
+        }
+        accumulate(rec, wv);
+    };
+    // general points: the full quadratic form on packed fp32 pairs
+    auto step_general = [&](const RecView rec, uint32_t zb, bool active) {
+        if (!active) return;
+        const float4 g0 = rec.chunk(0), g1 = rec.chunk(1), g2c = rec.chunk(2);
+        const float2 g2 = make_float2(g2c.x, g2c.y);
+        float wv[VOX];
+#pragma unroll
+        for (int h2 = 0; h2 < VOX / 2; ++h2) {
+            const int v0 = 2 * h2, v1 = v0 + 1;
+            const float2 dx = __fadd2_rn(make_float2(g0.x, g0.x), make_float2(-px[v0], -px[v1]));
+            const float2 dy = __fadd2_rn(make_float2(g0.y, g0.y), make_float2(-py[v0], -py[v1]));
+            const float2 dz = __fadd2_rn(make_float2(g0.z, g0.z), make_float2(-pz[v0], -pz[v1]));
+            float2 t1 = __fmul2_rn(make_float2(g1.x, g1.x), dx);
+            t1 = __ffma2_rn(make_float2(g1.w, g1.w), dy, t1);
+            t1 = __ffma2_rn(make_float2(g2.y, g2.y), dz, t1);
+            float2 t2 = __fmul2_rn(make_float2(g1.y, g1.y), dy);
+            t2 = __ffma2_rn(make_float2(g2.x, g2.x), dz, t2);
+            float2 q = __fmul2_rn(t1, dx);
+            q = __ffma2_rn(t2, dy, q);
+            q = __ffma2_rn(__fmul2_rn(make_float2(g1.z, g1.z), dz), dz, q);
+            const float E0 = ((zb >> v0) & 1u) ? ex2_approx(q.x) : 0.f;
+            const float E1 = ((zb >> v1) & 1u) ? ex2_approx(q.y) : 0.f;
+            wv[v0] = PROB ? g0.w * E0 : E0;
+            wv[v1] = PROB ? g0.w * E1 : E1;
+            if (PROB) {
+                zsum[v0] += wv[v0]; dens[v0] += E0; keep[v0] *= (1.f - E0);
+                zsum[v1] += wv[v1]; dens[v1] += E1; keep[v1] *= (1.f - E1);
+            }
+        }
+        accumulate(rec, wv);
+    };
+    // the column form is chosen per CTA (one vote); a CTA with any other thread takes the general form for all
+    const bool all_column = __syncthreads_and(column ? 1 : 0) != 0;
+    walk_tile<C>(pin, sm, binX0, binY0, binZ0, my_zshift, all_column, step_column, step_general);
 #ifdef GF_RENDER_TIMING
     const long long t_epi = clock64();
 #endif

@@ -73,9 +73,11 @@ struct RecView {
 // quad -- the box masks are separable, so ten ballots (4 x bits, 4 y bits, 2 z groups) and three selects produce all
 // 32 masks -- and walks its own bits in ascending order (the reference's summation order per voxel); the warp iterates
 // max-over-lanes popcount times instead of once per touching record.
-template <int C, class Step>
+// Two step functors: `step_fast` is used when `fast` (CTA-uniform) says every thread qualifies for it, `step` otherwise;
+// only the innermost loop exists twice.
+template <int C, class StepFast, class Step>
 __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &sm, int binX0, int binY0, int binZ0,
-                                          int my_zshift, Step &&step) {
+                                          int my_zshift, bool fast, StepFast &&step_fast, Step &&step) {
     constexpr int REC = rec_floats(C), ROW = RenderSmem<C>::ROW;
     constexpr int NT = kRenderThreads, NWARP = NT / 32, VOX = kVoxT;
     constexpr uint32_t VMASK = (1u << VOX) - 1u;
@@ -212,15 +214,28 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
 #endif
             // the warp takes as many steps as its busiest lane has hits in this batch
             const int nsteps = __reduce_max_sync(0xffffffffu, __popc(hits));
-#pragma unroll 1
-            for (int st = 0; st < nsteps; ++st) {
-                const bool act = hits != 0;
+            auto pop = [&](bool &act, RecView &rv, uint32_t &zb) {
+                act = hits != 0;
                 const int j = act ? __ffs(static_cast<int>(hits)) - 1 : 0;   // my lowest remaining hit
                 hits &= hits - 1;                                             // 0 stays 0
                 const uint32_t e = sm.list[k * kBatch + j].x;
-                RecView rv;
                 rv.addr = stage_base + static_cast<uint32_t>(j) * (ROW * 4);
-                step(rv, (e >> my_zshift) & VMASK, act);
+                zb = (e >> my_zshift) & VMASK;
+            };
+            if (fast) {
+#pragma unroll 1
+                for (int st = 0; st < nsteps; ++st) {
+                    bool act; RecView rv; uint32_t zb;
+                    pop(act, rv, zb);
+                    step_fast(rv, zb, act);
+                }
+            } else {
+#pragma unroll 1
+                for (int st = 0; st < nsteps; ++st) {
+                    bool act; RecView rv; uint32_t zb;
+                    pop(act, rv, zb);
+                    step(rv, zb, act);
+                }
             }
             __syncwarp();
 #ifdef GF_RENDER_TIMING

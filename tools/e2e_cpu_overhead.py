@@ -16,6 +16,15 @@ t1 = time.perf_counter()
 torch.cuda.synchronize()
 t2 = time.perf_counter()
 print("host time per forward_with_occupancy call: %.1f us (queue drained after %.1f us more per call)" % ((t1 - t0) / n * 1e6, (t2 - t1) / n * 1e6))
+with torch.no_grad():
+    for _ in range(5): m(d["pts"], d["means"], d["opa"], d["sem"], d["scales"], d["cov"]).argmax(dim=1).to(torch.uint8)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n): m(d["pts"], d["means"], d["opa"], d["sem"], d["scales"], d["cov"]).argmax(dim=1).to(torch.uint8)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+print("host time per forward + argmax + cast: %.1f us (device time per call %.1f us)" % ((t1 - t0) / n * 1e6, (t2 - t0) / n * 1e6))
 host = torch.empty(2_790_434, dtype=torch.float32).pin_memory()
 t0 = time.perf_counter()
 for _ in range(n): x = host.to(dev, non_blocking=True)

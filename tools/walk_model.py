@@ -27,9 +27,11 @@ def main(name="gs25600_solid"):
     rng = np.random.default_rng(0)
     nbx, nby = H // 8, W // 4
     bins = [(bx, by) for bx in range(nbx) for by in range(nby)]
-    sel = rng.choice(len(bins), size=300, replace=False)
+    sel = rng.choice(len(bins), size=int(sys.argv[2]) if len(sys.argv) > 2 else 300, replace=False)
     tot = {32: 0, 64: 0, 96: 0, "all": 0}
     win = {2: 0, 3: 0, 4: 0}
+    rowwin = {4: 0, 8: 0, 16: 0}                     # steps when a step may only touch rows [j0, j0 + R) of the batch
+    rows_per_step = {4: 0, 8: 0, 16: 0, 32: 0}
     lane_steps = 0; vox_pairs = 0; nrec = 0; uniform = 0
     for s in sel:
         bx, by = bins[s]
@@ -56,6 +58,20 @@ def main(name="gs25600_solid"):
             per = np.zeros((nb, 32), np.int64)           # hits of lane l in batch b
             for b in range(nb):
                 per[b] = hits[32 * b:32 * b + 32].sum(0)
+            for R in rows_per_step:
+                for b in range(nb):
+                    pend = [list(np.nonzero(hits[32 * b:32 * b + 32, l])[0]) for l in range(32)]
+                    while any(pend):
+                        j0 = min(q[0] for q in pend if q)
+                        touched = set()
+                        for q in pend:
+                            if q and q[0] < j0 + R:
+                                touched.add(q.pop(0))
+                        if R in rowwin:
+                            rowwin[R] += 1
+                        rows_per_step[R] += len(touched)
+                        if R == 32:
+                            rowwin.setdefault(32, 0); rowwin[32] += 1
             for Wn in win:
                 rem = per.copy()
                 for b in range(nb):
@@ -71,9 +87,11 @@ def main(name="gs25600_solid"):
         print("pool", k, "steps per warp", v / nw, "lane utilisation", lane_steps / (32.0 * v))
     for k, v in win.items():
         print("drain-oldest window", k, "steps per warp", v / nw)
+    for k, v in rowwin.items():
+        print("row window", k, "steps per warp", v / nw, "distinct rows per step", rows_per_step[k] / max(v, 1))
     print("warp-uniform steps per warp", uniform / nw)
     print("z-quad utilisation", vox_pairs / (4.0 * lane_steps))
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:])
+    main(*sys.argv[1:2])

@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
 #pragma unroll
     for (int v = 1; v < VOX; ++v) column = column && px[v] == px[0] && py[v] == py[0];
     const int my_zshift = 16 + VOX * lq;   // entry word: x mask [0,8) | y mask [8,12) | z mask [16,32)
+    int my_zlevel = Z0;                     // first z level of my quad: shift of a record's z-level mask
+    asm volatile("" : "+r"(my_zlevel));     // opaque: otherwise rebuilt from %tid / %ctaid in every step of the walk
 
     float2 acc[VOX][CP2];
     float zsum[VOX], dens[VOX], keep[VOX];
@@ -152,9 +154,12 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
     // dataset/transform_3d.py:484-499 without perturbation): the exponent is a quadratic
     // in dz alone, q = (cc*dz + B)*dz + A, with A and B evaluated once per record; the per-voxel part runs on
     // packed fp32 pairs (voxels (0,1) and (2,3) share each instruction).
-    auto step_column = [&](const RecView rec, uint32_t zb, bool active) {
+    auto step_column = [&](const RecView rec, uint32_t zb_entry, bool active) {
         if (!active) return;
         const float4 g0 = rec.chunk(0), g1 = rec.chunk(1), g2c = rec.chunk(2);
+        // base variant: the record's amplitude slot holds the z levels of the clipped box as a bit mask (pack kernel; the
+        // grid has at most 32 levels on this path, see `all_column`), so the list entry is not read at all
+        const uint32_t zb = PROB ? zb_entry : (__float_as_uint(g0.w) >> my_zlevel) & ((1u << VOX) - 1u);
         float wv[VOX];
         const float dx = g0.x - px[0], dy = g0.y - py[0];
         float t1 = g1.x * dx;
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
         accumulate(rec, wv);
     };
     // the column form is chosen per CTA (one vote); a CTA with any other thread takes the general form for all
-    const bool all_column = __syncthreads_and(column ? 1 : 0) != 0;
+    const bool all_column = __syncthreads_and((column && (PROB || D <= 32)) ? 1 : 0) != 0;
     walk_tile<C>(pin, sm, binX0, binY0, binZ0, my_zshift, all_column, step_column, step_general);
 #ifdef GF_RENDER_TIMING
     const long long t_epi = clock64();

@@ -41,7 +41,11 @@ constexpr int kSeg = 512;       // bin-list entries resolved per segment
 constexpr int kGeomFloats = 12; // mu(3) k(1) c6(6) pad(2)
 
 __host__ __device__ constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
-// one record = geometry + class vector, padded to a whole number of 128-byte lines
+// one record = geometry + class vector, padded to a whole number of 128-byte lines.  Forward records (render kernels), as
+// 16-byte chunks: 0 = mu(3), amplitude (base variant: z-level mask of the box) | 1 = exponent coefficients a b c d |
+// 2 = e f, classes 16 17 | 3..6 = classes 0..15 | 7 = classes 18 19, pad(2).  Classes 16 and 17 share the chunk of the
+// last two coefficients so that an 18-class step is six 16-byte shared loads instead of five and two 8-byte ones.  The raw
+// records of the backward keep the plain order: chunk 2 = e f 0 0, chunks 3..7 = classes 0..19.
 __host__ __device__ constexpr int rec_floats(int C) { return round_up(kGeomFloats + round_up(C, 4), 32); }
 
 // Integer box of one Gaussian, inclusive bounds packed lo | hi << 16 per axis; w = 1 when the

@@ -133,21 +133,27 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
 #endif
     // One step of a lane = one (record, my 4 voxels) evaluation: exponent and weights from the record's three geometry
     // chunks, then the class accumulation (4 x C/2 packed FMAs) with its class chunks read where they are used.
-    auto accumulate = [&](const RecView rec, const float (&wv)[VOX]) {
-#ifdef GF_EXPERIMENT_STUB_ACC   // experiment: how fast is the walk without the class accumulation? (results are wrong)
-        constexpr int kAccChunks = 1;
-#else
-        constexpr int kAccChunks = (C + 3) / 4;
-#endif
+    static_assert(C >= 16 && C <= 20, "forward record layout: class pairs 0..7 are always present");
+    auto accumulate = [&](const RecView rec, const float4 g2c, const float (&wv)[VOX]) {
+        // forward record layout (common.cuh): class pairs 0..7 in chunks 3..6, pair 8 in the coefficient chunk, pair 9 in chunk 7
 #pragma unroll
-        for (int c4 = 0; c4 < kAccChunks; ++c4) {
+        for (int c4 = 0; c4 < 4; ++c4) {
             const float4 s4 = rec.chunk(3 + c4);
 #pragma unroll
             for (int v = 0; v < VOX; ++v) {
                 const float2 ww = make_float2(wv[v], wv[v]);
                 acc[v][2 * c4] = __ffma2_rn(make_float2(s4.x, s4.y), ww, acc[v][2 * c4]);
-                if (2 * c4 + 1 < CP2) acc[v][2 * c4 + 1] = __ffma2_rn(make_float2(s4.z, s4.w), ww, acc[v][2 * c4 + 1]);
+                acc[v][2 * c4 + 1] = __ffma2_rn(make_float2(s4.z, s4.w), ww, acc[v][2 * c4 + 1]);
             }
+        }
+        if constexpr (CP2 > 8) {
+#pragma unroll
+            for (int v = 0; v < VOX; ++v) acc[v][8] = __ffma2_rn(make_float2(g2c.z, g2c.w), make_float2(wv[v], wv[v]), acc[v][8]);
+        }
+        if constexpr (CP2 > 9) {
+            const float4 s4 = rec.chunk(7);
+#pragma unroll
+            for (int v = 0; v < VOX; ++v) acc[v][9] = __ffma2_rn(make_float2(s4.x, s4.y), make_float2(wv[v], wv[v]), acc[v][9]);
         }
     };
     // My 4 points share x and y (voxel centres of one z column -- every shipped config,
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
                 zsum[v1] += wv[v1]; dens[v1] += E1; keep[v1] *= (1.f - E1);
             }
         }
-        accumulate(rec, wv);
+        accumulate(rec, g2c, wv);
     };
     // general points: the full quadratic form on packed fp32 pairs
     auto step_general = [&](const RecView rec, uint32_t zb, bool active) {
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(kRenderThreads, PROB ? 3 : GF_RENDER_CTAS) ren
                 zsum[v1] += wv[v1]; dens[v1] += E1; keep[v1] *= (1.f - E1);
             }
         }
-        accumulate(rec, wv);
+        accumulate(rec, g2c, wv);
     };
     // the column form is chosen per CTA (one vote); a CTA with any other thread takes the general form for all
     const bool all_column = __syncthreads_and((column && (PROB || D <= 32)) ? 1 : 0) != 0;

@@ -97,13 +97,16 @@ __global__ void __launch_bounds__(kPackThreads) pack_mask_kernel(const PackParam
         if (p.raw) {
             rec[1] = make_float4(a_, b_, c_, d_);
             rec[2] = make_float4(e_, f_, 0.f, 0.f);
-        } else {
-            rec[1] = make_float4(-0.5f * kLog2e * a_, -0.5f * kLog2e * b_, -0.5f * kLog2e * c_, -kLog2e * d_);
-            rec[2] = make_float4(-kLog2e * e_, -kLog2e * f_, 0.f, 0.f);
-        }
 #pragma unroll
-        for (int q = 0; q < 5; ++q)
-            if (q < nq) rec[3 + q] = make_float4(semv[4 * q], semv[4 * q + 1], semv[4 * q + 2], semv[4 * q + 3]);
+            for (int q = 0; q < 5; ++q)
+                if (q < nq) rec[3 + q] = make_float4(semv[4 * q], semv[4 * q + 1], semv[4 * q + 2], semv[4 * q + 3]);
+        } else {   // forward layout (common.cuh): classes 16, 17 ride in the coefficient chunk
+            rec[1] = make_float4(-0.5f * kLog2e * a_, -0.5f * kLog2e * b_, -0.5f * kLog2e * c_, -kLog2e * d_);
+            rec[2] = make_float4(-kLog2e * e_, -kLog2e * f_, semv[16], semv[17]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rec[3 + q] = make_float4(semv[4 * q], semv[4 * q + 1], semv[4 * q + 2], semv[4 * q + 3]);
+            if (nq > 4) rec[7] = make_float4(semv[18], semv[19], 0.f, 0.f);
+        }
     }
 
     // ---- supertile masks: per-warp words assembled in shared memory, stored by all lanes ------------

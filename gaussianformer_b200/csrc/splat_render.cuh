@@ -109,13 +109,20 @@ __device__ __forceinline__ void render_one_point(const RenderParams &p, long lon
                 dens += E;
                 keep *= (1.f - E);
             }
+            // forward record layout (common.cuh): classes 0..15 in chunks 3..6, 16 17 in the coefficient chunk, 18 19 in chunk 7
 #pragma unroll
-            for (int c4 = 0; c4 < (REC - kGeomFloats) / 4; ++c4) {
+            for (int c4 = 0; c4 < 4; ++c4) {
                 const float4 s4 = __ldg(r4 + 3 + c4);
                 const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (c4 * 4 + k < C) acc[c4 * 4 + k] = fmaf(sv[k], w, acc[c4 * 4 + k]);
+                for (int k = 0; k < 4; ++k) acc[c4 * 4 + k] = fmaf(sv[k], w, acc[c4 * 4 + k]);
+            }
+            if constexpr (C > 16) acc[16] = fmaf(g2.z, w, acc[16]);
+            if constexpr (C > 17) acc[17] = fmaf(g2.w, w, acc[17]);
+            if constexpr (C > 18) {
+                const float4 s4 = __ldg(r4 + 7);
+                acc[18] = fmaf(s4.x, w, acc[18]);
+                if constexpr (C > 19) acc[19] = fmaf(s4.y, w, acc[19]);
             }
         }
     }

@@ -216,10 +216,10 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
             const int nsteps = __reduce_max_sync(0xffffffffu, __popc(hits));
             auto pop = [&](bool &act, RecView &rv, uint32_t &zb) {
                 act = hits != 0;
-                const int j = act ? __ffs(static_cast<int>(hits)) - 1 : 0;   // my lowest remaining hit
+                const int jraw = __ffs(static_cast<int>(hits)) - 1;          // my lowest remaining hit; -1 when I have none
                 hits &= hits - 1;                                             // 0 stays 0
-                const uint32_t e = sm.list[k * kBatch + j].x;
-                rv.addr = stage_base + static_cast<uint32_t>(j) * (ROW * 4);
+                rv.addr = stage_base + static_cast<uint32_t>(jraw * (ROW * 4));   // an inactive lane never dereferences it
+                const uint32_t e = sm.list[k * kBatch + (act ? jraw : 0)].x;
                 zb = (e >> my_zshift) & VMASK;
             };
             if (fast) {

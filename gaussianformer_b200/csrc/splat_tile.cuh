@@ -223,7 +223,7 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
                 zb = (e >> my_zshift) & VMASK;
             };
             if (fast) {
-#pragma unroll 1
+#pragma unroll 2
                 for (int st = 0; st < nsteps; ++st) {
                     bool act; RecView rv; uint32_t zb;
                     pop(act, rv, zb);

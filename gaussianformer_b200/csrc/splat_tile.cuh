@@ -32,6 +32,7 @@ struct RenderSmem {
     static constexpr int NT = kRenderThreads;
     alignas(128) float stage[kRing][kBatch * ROW];
     alignas(8) uint2 list[kQuadSeg + kBatch];  // x: box relative to the bin as bit masks, y: Gaussian index
+    uint32_t hitw[kQuadSeg / kBatch + 1][16];  // per batch: bit j of word i = entry j covers x position i (0..7), y position i-8 (8..11), z quad i-12 (12..15)
     alignas(8) uint64_t bar_full[kRing];       // records of the slot have landed (one cp.async arrival per thread)
     alignas(8) uint64_t bar_empty[kRing];      // every warp is done with the slot (one arrival per warp)
     int warp_count[2][NT / 32];
@@ -70,8 +71,8 @@ struct RecView {
 // Lane-private traversal: a Gaussian's box covers only part of a warp's 4 x 4 x 8 footprint (17.7 of 32 lanes on the
 // nuScenes workload), so marching all lanes through every record that touches the footprint leaves almost half of them
 // idle in every step.  Instead each lane gets the bit mask of the records of the batch that cover ITS column and z
-// quad -- the box masks are separable, so ten ballots (4 x bits, 4 y bits, 2 z groups) and three selects produce all
-// 32 masks -- and walks its own bits in ascending order (the reference's summation order per voxel); the warp iterates
+// quad -- the box masks are separable, so 16 ballots per batch and CTA (8 x bits, 4 y bits, 4 z quads; three word loads
+// and two ANDs per lane) produce all 128 masks -- and walks its own bits in ascending order (the reference's summation order per voxel); the warp iterates
 // max-over-lanes popcount times instead of once per touching record.
 // Two step functors: `step_fast` is used when `fast` (CTA-uniform) says every thread qualifies for it, `step` otherwise;
 // only the innermost loop exists twice.
@@ -156,6 +157,21 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
         // pad the last batch with empty entries (all-zero masks, so nobody visits them)
         if (tid < kBatch && nlist + tid < ((nlist + kBatch - 1) / kBatch) * kBatch) sm.list[nlist + tid] = make_uint2(0u, 0u);
         __syncthreads();
+        // The box masks are separable, so 16 ballots per batch -- taken ONCE per CTA, the batches dealt to the four warps --
+        // transpose them into 16 words (which entries cover x position i / y position i / z quad i); a lane's hit mask of a
+        // batch is then the AND of three of those words (ten ballots per warp and batch before: 9 % of Phase B).
+        for (int b = warp; b < (nlist + kBatch - 1) / kBatch; b += NWARP) {
+            const uint32_t ex = sm.list[b * kBatch + lane].x;
+            uint32_t mine = 0u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const bool covers = i < 12 ? ((ex >> i) & 1u) != 0u : ((ex >> (16 + VOX * (i - 12))) & VMASK) != 0u;
+                const uint32_t w = __ballot_sync(0xffffffffu, covers);
+                if (lane == i) mine = w;
+            }
+            if (lane < 16) sm.hitw[b][lane] = mine;
+        }
+        __syncthreads();
 #ifdef GF_RENDER_TIMING
         const long long tB0 = clock64();
         if (tid == 0) sm.t_phase[1] += static_cast<unsigned long long>(tB0 - tA0);
@@ -191,19 +207,8 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
             // bit j of `hits`: record j of this batch covers my column and my z quad (padded entries are all-zero)
             uint32_t hits;
             {
-                const uint32_t ex = sm.list[k * kBatch + lane].x;
-                const int xh = 4 * (warp & 1), zg = 16 + 2 * VOX * (warp >> 1);
-                const int sx = lane >> 3, sy = (lane >> 1) & 3;
-                uint32_t bx[4], by[4], bz[2];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    bx[i] = __ballot_sync(0xffffffffu, (ex >> (xh + i)) & 1u);
-                    by[i] = __ballot_sync(0xffffffffu, (ex >> (8 + i)) & 1u);
-                }
-#pragma unroll
-                for (int q = 0; q < 2; ++q) bz[q] = __ballot_sync(0xffffffffu, ((ex >> (zg + VOX * q)) & VMASK) != 0u);
-                hits = (sx == 0 ? bx[0] : sx == 1 ? bx[1] : sx == 2 ? bx[2] : bx[3]) &
-                       (sy == 0 ? by[0] : sy == 1 ? by[1] : sy == 2 ? by[2] : by[3]) & ((lane & 1) ? bz[1] : bz[0]);
+                const uint32_t *hw = sm.hitw[k];
+                hits = hw[4 * (warp & 1) + (lane >> 3)] & hw[8 + ((lane >> 1) & 3)] & hw[12 + 2 * (warp >> 1) + (lane & 1)];
             }
 #ifdef GF_RENDER_TIMING
             const long long tw0 = clock64();

@@ -1,7 +1,7 @@
 set +e
-out=gpurun_out/r02_za; mkdir -p $out
+out=gpurun_out/r02_zb; mkdir -p $out
 timeout 900 python -m pytest tests/test_splat_gpu.py tests/test_cabi_gpu.py tests/test_batch_fused_gpu.py tests/test_parity_full_gpu.py -m gpu -q -x 2>&1 | tail -2
 for rep in 1 2; do
-  echo "== column loop unrolled by 2 (default lib)"; timeout 300 python tools/time_render.py
+  echo "== CTA-level hit words (default lib)"; timeout 300 python tools/time_render.py
   echo "== prev (HEAD)"; GF_B200_LIB=$PWD/gaussianformer_b200/csrc/variants/libgf_b200_prev.so timeout 300 python tools/time_render.py
 done

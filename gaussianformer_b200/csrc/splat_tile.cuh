@@ -157,6 +157,23 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
         // pad the last batch with empty entries (all-zero masks, so nobody visits them)
         if (tid < kBatch && nlist + tid < ((nlist + kBatch - 1) / kBatch) * kBatch) sm.list[nlist + tid] = make_uint2(0u, 0u);
         __syncthreads();
+        const int nchunks = (nlist + kBatch - 1) / kBatch;
+        auto issue = [&](int k, uint32_t b_index) {  // batch k of this segment -> ring slot b_index % kRing
+            const int slot = b_index % kRing;
+            const uint32_t use = b_index / kRing;
+            if (use > 0) mbar_wait(&sm.bar_empty[slot], (use - 1) & 1);   // previous occupant released by all warps
+#pragma unroll
+            for (int q = 0; q < (kBatch * 8 + NT - 1) / NT; ++q) {     // 32 records x 8 x 16 B = 256 copies
+                const int piece = tid + NT * q, row = piece >> 3, col = (piece & 7) * 4;
+                if (piece < kBatch * 8 && k * kBatch + row < nlist) {
+                    const uint32_t g = sm.list[k * kBatch + row].y;
+                    cp_async16(&sm.stage[slot][row * ROW + col], p.records + static_cast<size_t>(g) * REC + col);
+                }
+            }
+            cp_async_arrive_on(&sm.bar_full[slot]);
+        };
+#pragma unroll 1
+        for (int k = 0; k < kRing - 1 && k < nchunks; ++k) issue(k, gb + k);
         // The box masks are separable, so 16 ballots per batch -- taken ONCE per CTA, the batches dealt to the four warps --
         // transpose them into 16 words (which entries cover x position i / y position i / z quad i); a lane's hit mask of a
         // batch is then the AND of three of those words (ten ballots per warp and batch before: 9 % of Phase B).
@@ -180,23 +197,6 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
         // ======================= Phase B: stream records and accumulate ==============================
         // No CTA-wide barrier in this loop: full[] / empty[] mbarriers let the four warps drift apart by
         // up to kRing-2 batches, so a warp whose footprint is touched by few records does not wait.
-        const int nchunks = (nlist + kBatch - 1) / kBatch;
-        auto issue = [&](int k, uint32_t b_index) {  // batch k of this segment -> ring slot b_index % kRing
-            const int slot = b_index % kRing;
-            const uint32_t use = b_index / kRing;
-            if (use > 0) mbar_wait(&sm.bar_empty[slot], (use - 1) & 1);   // previous occupant released by all warps
-#pragma unroll
-            for (int q = 0; q < (kBatch * 8 + NT - 1) / NT; ++q) {     // 32 records x 8 x 16 B = 256 copies
-                const int piece = tid + NT * q, row = piece >> 3, col = (piece & 7) * 4;
-                if (piece < kBatch * 8 && k * kBatch + row < nlist) {
-                    const uint32_t g = sm.list[k * kBatch + row].y;
-                    cp_async16(&sm.stage[slot][row * ROW + col], p.records + static_cast<size_t>(g) * REC + col);
-                }
-            }
-            cp_async_arrive_on(&sm.bar_full[slot]);
-        };
-#pragma unroll 1
-        for (int k = 0; k < kRing - 1 && k < nchunks; ++k) issue(k, gb + k);
 #pragma unroll 1
         for (int k = 0; k < nchunks; ++k, ++gb) {
 #ifdef GF_RENDER_TIMING
@@ -235,7 +235,7 @@ __device__ __forceinline__ void walk_tile(const RenderParams &p, RenderSmem<C> &
                     step_fast(rv, zb, act);
                 }
             } else {
-#pragma unroll 1
+#pragma unroll 2
                 for (int st = 0; st < nsteps; ++st) {
                     bool act; RecView rv; uint32_t zb;
                     pop(act, rv, zb);

@@ -1,5 +1,5 @@
 set +e
-out=gpurun_out/r02_u; mkdir -p $out
+out=gpurun_out/r02_ze; mkdir -p $out
 t0=$(date +%s)
 timeout 1500 python -m pytest tests -m gpu -q -x > $out/pytest.log 2>&1; echo "pytest rc=$?" >> $out/pytest.log; tail -3 $out/pytest.log
 t1=$(date +%s); echo "pytest seconds $((t1-t0))"

@@ -1,5 +1,5 @@
 set +e
-out=gpurun_out/r02_x; mkdir -p $out
+out=gpurun_out/r02_zf; mkdir -p $out
 # final kernels: launch list of the bench step (cold-cache, serialised; direct launches so that ncu sees the kernels) and
 # one --set full capture of the render kernel at 1 and 4 samples per launch
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file $out/launches_fwd.csv python bench.py --steps 6 --warmup 3 --no-extras --no-graph > $out/ncu_l1.log 2>&1

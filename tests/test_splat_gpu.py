@@ -24,7 +24,9 @@ def _run(kw, inp, variant, requires_grad=False, validate=True):
     ("tiny", 0, False, None),
     ("tiny", 1, True, None),
     ("tiny", 2, True, dict(dims=(37, 21, 6), pc_min=(-9.0, -5.0, -1.5))),      # D % 4 != 0, ragged bins
-    ("tiny", 3, False, dict(dims=(16, 8, 40), pc_min=(-4.0, -2.0, -10.0))),     # several z chunks
+    ("tiny", 3, False, dict(dims=(16, 8, 40), pc_min=(-4.0, -2.0, -10.0))),     # several z chunks; > 32 levels: no z-level mask in the record
+    ("tiny", 5, False, dict(dims=(16, 8, 32), pc_min=(-4.0, -2.0, -8.0))),      # two z chunks, z-level mask uses all 32 bits
+    ("tiny", 6, False, dict(dims=(12, 8, 24), pc_min=(-3.0, -2.0, -6.0))),      # second chunk half empty
     ("tiny", 4, True, dict(G=1)),
     ("gs25600_solid", 0, True, dict(G=3000)),                                   # full grid + empty Gaussian
 ])

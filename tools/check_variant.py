@@ -1,6 +1,6 @@
-"""Quick hardware check of whatever render variant the environment selects (GF_B200_RENDER / GF_B200_LIB / GF_B200_ST):
+"""Quick hardware check of whatever render variant the environment selects (GF_B200_LIB / GF_B200_ST):
 one full-grid sample on exact voxel centres (the fast path of every tile kernel) and one tiny sample (edge tiles, generic
-fallbacks) against the fp64 oracle, then a short timing.  Usage: GF_B200_RENDER=tc3 python tools/check_variant.py"""
+fallbacks) against the fp64 oracle, then a short timing.  Usage: GF_B200_LIB=<variant library> python tools/check_variant.py"""
 import os
 import sys
 import time

@@ -2,10 +2,9 @@
 # One GPU visit: parity tests, then A/B bench lines of the render-kernel variants (libraries built by
 # tools/build_variant.py), optionally ncu captures.  Usage (through gpurun):
 #   bash tools/gpu_round.sh <tag> "<variants>" [tests] [ncu] [full]
-# A variant is `default`, the name of a library built by tools/build_variant.py (e.g. `pipe2` after
-# `python tools/build_variant.py pipe2 -DGF_TILE_PIPE=2`), `st:<n>` for GF_B200_ST=<n>, and `<selector>@<library>` combines
-# an environment selector with a variant library (e.g. `render:tc3@tc3half` after
-# `python tools/build_variant.py tc3half -DGF_TC3_HALF=1`).
+# A variant is `default`, the name of a library built by tools/build_variant.py (e.g. `ring6` after
+# `python tools/build_variant.py ring6 -DGF_TILE_RING=6`), `st:<n>` for GF_B200_ST=<n>, and `<selector>@<library>` combines
+# an environment selector with a variant library (e.g. `st:8@ring6`).
 # Every non-default variant first runs the splat parity tests, then two bench lines.
 set +e
 tag=${1:-x}; variants=${2:-default}; shift 2
@@ -20,7 +19,7 @@ for what in "$@"; do
   fi
 done
 for v in $variants; do
-  unset GF_B200_LIB GF_B200_RENDER GF_B200_ST
+  unset GF_B200_LIB GF_B200_ST
   # a variant is <selector>[@<library>]: selector = default | render:<x> | st:<n> | <library>
   sel=${v%%@*}; lib=""
   if [ "$sel" != "$v" ]; then lib=${v#*@}; fi
@@ -42,7 +41,7 @@ except Exception as e:
 PY
   done
 done
-unset GF_B200_LIB GF_B200_RENDER GF_B200_ST
+unset GF_B200_LIB GF_B200_ST
 for what in "$@"; do
   if [ $what = ncu ]; then
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
